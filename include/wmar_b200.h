@@ -1,0 +1,187 @@
+/*
+ * wmar_b200.h -- C-ABI of the B200-native watermarked autoregressive image-generation hot path.
+ *
+ * Drop-in boundary for the hot path of facebookresearch/wmar (reference file:line cited per entry point).
+ * Plain pointers and sizes only; no torch / C++ types.  All `d_` pointers are DEVICE pointers on the current CUDA
+ * device, all `h_` pointers are HOST pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream).  Every function returns 0 on success or a negative wmar_status; the message of the last failure on the
+ * calling thread is available from wmar_last_error().  Nothing here throws, exits, or synchronises the device unless
+ * stated.  One handle per (process, device); calls on one handle must be serialised by the caller
+ * (the reference is single-threaded per GPU as well).
+ *
+ * Ownership: the caller owns every buffer it passes in.  Handles own only their scratch (KV cache, activations,
+ * split-K workspaces) and BORROW weight pointers: weights live in the caller's tensors (the reference patches
+ * nn.Module weights after construction -- generate.py:327-332 -- so the host shim re-packs and calls *_create again
+ * after any patch).
+ */
+#ifndef WMAR_B200_H
+#define WMAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum wmar_status {
+    WMAR_OK = 0,
+    WMAR_ERR_INVALID = -1, /* bad argument (shape / enum / NULL)            */
+    WMAR_ERR_CUDA = -2,    /* CUDA runtime error, see wmar_last_error()      */
+    WMAR_ERR_RANGE = -3,   /* context sum / token id outside the table       */
+    WMAR_ERR_NOMEM = -4,
+    WMAR_ERR_SHORT = -5    /* detect(): len(codes) <= context size (reference raises ValueError,
+                              gentime_watermark.py:287-291) */
+};
+
+/* wmar/watermarking/gentime_watermark.py:94-106 */
+enum wmar_seed_strategy { WMAR_SEED_FIXED = 0, WMAR_SEED_LINEAR = 1, WMAR_SEED_SPATIAL = 2 };
+enum wmar_split_strategy { WMAR_SPLIT_RANDOM = 0, WMAR_SPLIT_RANDOM_STRATIFIED = 1 };
+
+#define WMAR_SALT_KEY 15485863ull /* gentime_watermark.py:121 */
+
+int wmar_version(void);
+const char *wmar_last_error(void);
+/* number of kernels launched by this library since load (all handles); bench.py reports it as gpu_launches */
+uint64_t wmar_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Greenlist engine.  Replaces GentimeWatermark._split_with_seed + _get_greenlist_ids_for_context
+ * (gentime_watermark.py:161-226): seed = (salt * sum(ctx)) mod (2^64-1) -> MT19937 (torch CPU generator) ->
+ * randperm(alive), randperm(dead) -> first int(n_alive*gamma) alive + int(V*gamma)-that dead ids are green.
+ * Output: a bitmask TABLE [n_rows][words], words = ceil(V/32), row s = greenlist for context SUM s (only the sum
+ * enters the seed); FIXED seeding uses n_rows = 1 (seed 0).  Bit (id & 31) of word (id >> 5) is set iff id is green.
+ * alive/dead are int64 id lists exactly as armm_wrapper.py:42-55 builds them (alive in file order, dead sorted).
+ * ---------------------------------------------------------------------------------------------------------- */
+int wmar_greenlist_build_host(int64_t vocab_size, double gamma, int split_strategy, int seed_strategy,
+                              uint64_t salt_key, const int64_t *h_alive, int64_t n_alive, const int64_t *h_dead,
+                              int64_t n_dead, int64_t n_rows, uint32_t *h_table_out, int n_threads);
+/* same table built by a CUDA kernel (one CTA per row) straight into HBM */
+int wmar_greenlist_build_device(int64_t vocab_size, double gamma, int split_strategy, int seed_strategy,
+                                uint64_t salt_key, const int64_t *d_alive, int64_t n_alive, const int64_t *d_dead,
+                                int64_t n_dead, int64_t n_rows, uint32_t *d_table_out, void *stream);
+
+/* Watermark description shared by the operators below. */
+typedef struct wmar_wm_params {
+    const uint32_t *d_table; /* [n_rows][ceil(V/32)] from wmar_greenlist_build_*; NULL = no watermark */
+    int64_t n_rows;
+    int64_t vocab_size;
+    int seed_strategy;   /* wmar_seed_strategy */
+    int context_size;    /* h */
+    int spatial_dim;     /* 16 (Taming/RAR) or 32 (Chameleon), gentime_watermark.py:153 */
+    float delta;
+    double gamma;
+} wmar_wm_params;
+
+/*
+ * The logit-processor operator: GentimeWatermark._process_logits (gentime_watermark.py:229-271), the callback invoked
+ * at mingpt.py:350, rar.py:451, chameleon.py:320.  In place: logits[b, green(ctx_b)] += delta.  Rows whose history is
+ * shorter than the context are left untouched (the reference swallows the ValueError, :268-270).
+ * d_past_ids int64 [B][t] with row stride past_stride (elements); d_logits fp32 [B][V] contiguous.
+ */
+int wmar_wm_process_logits(const wmar_wm_params *wm, const int64_t *d_past_ids, int64_t B, int64_t t,
+                           int64_t past_stride, float *d_logits, void *stream);
+
+/* Sampling parameters of one step (mingpt.py:326-368 / rar.py:446-454). */
+typedef struct wmar_sample_params {
+    float temperature;
+    int top_k;        /* <= 0: no top-k  (HF TopKLogitsWarper, keeps ties)                         */
+    float top_p;      /* <= 0 or >= 1: no top-p (HF TopPLogitsWarper, ascending sort, keep last)    */
+    int greedy;       /* 1: first arg-max of softmax (sample_logits=False, mingpt.py:360-361)      */
+    uint64_t seed;    /* Philox key used when d_noise == NULL and !greedy                          */
+} wmar_sample_params;
+
+/*
+ * Fused operator for one step on given logits: +delta on green -> /T -> top-k -> top-p -> softmax -> multinomial.
+ * d_noise fp32 [B][V] = q ~ Exp(1) as drawn by torch.multinomial (argmax(p / q)); NULL = in-kernel Philox.
+ * d_logits is not modified.  d_out_ids int64 [B].
+ */
+int wmar_wm_sample(const wmar_wm_params *wm, const wmar_sample_params *sp, const int64_t *d_past_ids, int64_t B,
+                   int64_t t, int64_t past_stride, const float *d_logits, const float *d_noise, int64_t *d_out_ids,
+                   void *stream);
+
+/*
+ * Detector: GentimeWatermark.detect + _score_ngrams_in_passage (gentime_watermark.py:285-344).  One CTA per passage.
+ * d_codes int64 [B][L].  Outputs (device, any may be NULL): n_green int32[B], n_scored int32[B] (unique n-grams),
+ * z f64[B] = (n_green - gamma T)/sqrt(T gamma (1-gamma)), p f64[B] = I_gamma(n_green, T - n_green + 1) = P[Bin(T,gamma)
+ * >= n_green] (scipy.special.betainc at :338), mask int8 [B][mask_stride] (-1 unscored/repeat, 0 red, 1 green; entry
+ * layout as the reference's list: h leading -1 then one entry per n-gram), mask_len int32[B].
+ * Returns WMAR_ERR_SHORT if L - h < 1.
+ */
+int wmar_detect(const wmar_wm_params *wm, const int64_t *d_codes, int64_t B, int64_t L, int32_t *d_n_green,
+                int32_t *d_n_scored, double *d_z, double *d_p, int8_t *d_mask, int64_t mask_stride,
+                int32_t *d_mask_len, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Taming minGPT decode engine.  Replaces sample_with_past (mingpt.py:326-368) + GPT.forward_with_past (:183-214) +
+ * Block / CausalSelfAttention (:42-122) with the watermark operator and the sampler fused behind the lm_head, the
+ * whole `steps`-token loop enqueued on `stream` with no host round trip per token.
+ * Weights are fp32, borrowed, passed as a table of device pointers in this order:
+ *   [0] tok_emb [V][d]   [1] pos_emb [block_size][d]
+ *   per layer l (12 entries, base 2 + 12 l): ln1.weight, ln1.bias, Wqkv [3d][d] (rows: query|key|value), bqkv [3d],
+ *     Wproj [d][d], bproj, ln2.weight, ln2.bias, W1 [4d][d], b1, W2 [d][4d], b2
+ *   then ln_f.weight, ln_f.bias, head.weight [V][d]
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct wmar_gpt_config {
+    int vocab_size, block_size, n_layer, n_head, n_embd;
+    int max_batch; /* rows per sampling call, <= 16 in this version */
+} wmar_gpt_config;
+
+typedef struct wmar_gpt wmar_gpt;
+
+int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, int n_weights, wmar_gpt **out);
+void wmar_gpt_destroy(wmar_gpt *g);
+/*
+ * d_cond int64 [B] class ids (the conditioning token, taming_wrapper.py:62); d_noise fp32 [steps][B][V] or NULL;
+ * d_out_codes int64 [B][steps].  d_out_logits (optional, may be NULL) fp32 [steps][B][V] receives the raw lm_head
+ * logits of every step (before the watermark), for numerics tests.
+ */
+int wmar_gpt_sample(wmar_gpt *g, const wmar_wm_params *wm, const wmar_sample_params *sp, const int64_t *d_cond,
+                    int64_t B, int64_t steps, const float *d_noise, int64_t *d_out_codes, float *d_out_logits,
+                    void *stream);
+/* algorithmic bytes moved by one sampling call of B rows x steps (weights once per step + KV), for the roofline */
+double wmar_gpt_algorithmic_bytes(const wmar_gpt *g, int64_t B, int64_t steps);
+/* kernels launched per decode step by this engine */
+int wmar_gpt_launches_per_step(const wmar_gpt *g);
+
+/* A single skinny GEMM (the dominant kernel), exposed for unit tests and the roofline microbenchmark:
+ * y[16][N] = x[16][K] . W[N][K]^T + bias, fp32 in/out, 3xTF32 tensor-core products with fp32 accumulation. */
+int wmar_skinny_gemm(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t N, int64_t K,
+                     int split_k, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * VQGAN tokenizer (Taming / Chameleon family and MaskGIT / RAR family).
+ * Replaces codes_to_images / images_to_codes (taming_wrapper.py:79-92, rar_wrapper.py:109-128) and below them
+ * Decoder/Encoder.forward (taming model.py:343-538; maskgit_vqgan.py:160-245), the quant convs (vqgan.py:64-73)
+ * and the codebook arg-min / gather (quantize.py:272-331; maskgit_vqgan.py:283-321).
+ * Weights: fp32, borrowed, as a table of device pointers in the order produced by the host shim
+ * (wmar_b200/models/vqgan_pack.py documents it; conv weights are pre-transposed to [Cout][ky][kx][Cin]).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct wmar_vqgan_config {
+    int family;            /* 0 = Taming/Chameleon (attention, conv down, biases), 1 = MaskGIT (RAR)      */
+    int ch;                /* base channels (128)                                                          */
+    int n_levels;          /* len(ch_mult)                                                                 */
+    int ch_mult[8];
+    int num_res_blocks;
+    int attn_resolution;   /* Taming: resolution at which AttnBlocks are inserted (16); 0 = none           */
+    int resolution;        /* image side (256)                                                             */
+    int z_channels;        /* 256                                                                          */
+    int embed_dim;         /* codebook vector dim (256)                                                    */
+    int n_embed;           /* codebook size                                                                */
+    int max_batch;
+    int precision;         /* 0 = 3xTF32 (fp32-faithful), 1 = 1xTF32 (the reference's cuDNN default)       */
+} wmar_vqgan_config;
+
+typedef struct wmar_vqgan wmar_vqgan;
+
+int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights, int n_weights, wmar_vqgan **out);
+void wmar_vqgan_destroy(wmar_vqgan *v);
+/* d_codes int64 [B][s*s] -> d_images fp32 [B][3][S][S] (NCHW, [-1,1], clamped) */
+int wmar_vqgan_decode(wmar_vqgan *v, const int64_t *d_codes, int64_t B, float *d_images, void *stream);
+/* d_images fp32 [B][3][S][S] in [-1,1] -> d_codes int64 [B][s*s] */
+int wmar_vqgan_encode(wmar_vqgan *v, const float *d_images, int64_t B, int64_t *d_codes, void *stream);
+double wmar_vqgan_flops(const wmar_vqgan *v, int decode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WMAR_B200_H */
