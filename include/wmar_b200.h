@@ -85,7 +85,8 @@ int wmar_wm_process_logits(const wmar_wm_params *wm, const int64_t *d_past_ids, 
 typedef struct wmar_sample_params {
     float temperature;
     int top_k;        /* <= 0: no top-k  (HF TopKLogitsWarper, keeps ties)                         */
-    float top_p;      /* <= 0 or >= 1: no top-p (HF TopPLogitsWarper, ascending sort, keep last)    */
+    double top_p;     /* <= 0 or >= 1: no top-p (HF TopPLogitsWarper, ascending sort, keep last); double so
+                         that (float)(1 - top_p) equals torch's scalar cast                        */
     int greedy;       /* 1: first arg-max of softmax (sample_logits=False, mingpt.py:360-361)      */
     uint64_t seed;    /* Philox key used when d_noise == NULL and !greedy                          */
 } wmar_sample_params;
@@ -98,6 +99,10 @@ typedef struct wmar_sample_params {
 int wmar_wm_sample(const wmar_wm_params *wm, const wmar_sample_params *sp, const int64_t *d_past_ids, int64_t B,
                    int64_t t, int64_t past_stride, const float *d_logits, const float *d_noise, int64_t *d_out_ids,
                    void *stream);
+
+/* Reads and clears the device-side error flag set by the operators above (synchronises `stream`):
+ * WMAR_OK, or WMAR_ERR_RANGE when a context sum fell outside the table / the top-p candidate set overflowed. */
+int wmar_check_device_flag(void *stream);
 
 /*
  * Detector: GentimeWatermark.detect + _score_ngrams_in_passage (gentime_watermark.py:285-344).  One CTA per passage.

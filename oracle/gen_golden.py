@@ -170,7 +170,7 @@ def gen_gpt():
     out = {}
     alive, dead = wm.alive_dead(wm.load_ids(os.path.join(REF, "assets/vqgan_alive_ids.txt")), 16384)
     vq = {"alive_ids": torch.from_numpy(alive), "dead_ids": torch.from_numpy(dead), "embedding": torch.zeros(4, 4)}
-    cfgs = {"tiny": dict(vocab_size=16384, block_size=256, n_layer=2, n_head=4, n_embd=128, steps=24, B=4),
+    cfgs = {"tiny": dict(vocab_size=16384, block_size=256, n_layer=2, n_head=2, n_embd=128, steps=24, B=4),
             "narrow": dict(vocab_size=16384, block_size=256, n_layer=3, n_head=6, n_embd=384, steps=48, B=16)}
     for name, c in cfgs.items():
         steps, B = c.pop("steps"), c.pop("B")

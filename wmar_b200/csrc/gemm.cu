@@ -1,0 +1,82 @@
+// Launchers for the skinny GEMM + the standalone C-ABI entry used by unit tests and the roofline microbenchmark.
+#include "gemm.cuh"
+
+namespace wmar {
+
+template <int PRO, int EPI>
+static int launch_t(const GemmArgs &a, cudaStream_t stream) {
+    dim3 grid((unsigned)(a.N / GEMM_NT), (unsigned)a.splits);
+    skinny_gemm_kernel<PRO, EPI><<<grid, GEMM_THREADS, 0, stream>>>(a);
+    WMAR_LAUNCH_CHECK();
+    return WMAR_OK;
+}
+
+int launch_skinny_gemm(int pro, int epi, const GemmArgs &a, cudaStream_t stream) {
+    WMAR_REQUIRE(a.N % GEMM_NT == 0, "N must be a multiple of 64");
+    WMAR_REQUIRE(a.splits >= 1 && a.K % (a.splits * GEMM_WARPS * GEMM_KI) == 0, "K must be a multiple of splits*128");
+    WMAR_REQUIRE(a.splits == 1 || (a.ws != nullptr && a.counters != nullptr), "split-K needs a workspace");
+    WMAR_REQUIRE(a.ldx % 4 == 0 && a.ldy % 4 == 0, "row strides must be multiples of 4 floats");
+#define WMAR_CASE(P, E) \
+    if (pro == P && epi == E) return launch_t<P, E>(a, stream);
+    WMAR_CASE(PRO_NONE, EPI_STORE)
+    WMAR_CASE(PRO_NONE, EPI_RESID)
+    WMAR_CASE(PRO_NONE, EPI_GATE_RESID)
+    WMAR_CASE(PRO_NONE, EPI_GELU)
+    WMAR_CASE(PRO_LN, EPI_STORE)
+    WMAR_CASE(PRO_LN, EPI_GELU)
+    WMAR_CASE(PRO_ADALN, EPI_STORE)
+    WMAR_CASE(PRO_ADALN, EPI_GELU)
+#undef WMAR_CASE
+    return set_error(WMAR_ERR_INVALID, "unsupported GEMM prologue/epilogue combination%s%s");
+}
+
+int pick_splits(int N, int K, int n_sms) {
+    const int tiles = N / GEMM_NT;
+    const int target = 2 * n_sms - 16;  // about one full wave at two CTAs per SM
+    int best = 1;
+    for (int s = 1; s <= 64; s++) {
+        if (K % (s * GEMM_WARPS * GEMM_KI) != 0) continue;
+        best = s;
+        if (tiles * s >= target) break;
+    }
+    return best;
+}
+
+}  // namespace wmar
+
+using namespace wmar;
+
+namespace {
+float *g_ws = nullptr;
+unsigned *g_counters = nullptr;
+size_t g_ws_bytes = 0, g_counter_n = 0;
+}  // namespace
+
+extern "C" int wmar_skinny_gemm(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t N,
+                                int64_t K, int split_k, void *stream) {
+    WMAR_REQUIRE(d_x && d_w && d_y && N > 0 && K > 0, "bad arguments");
+    WMAR_REQUIRE(N % GEMM_NT == 0 && K % (GEMM_WARPS * GEMM_KI) == 0, "N % 64 == 0 and K % 128 == 0 required");
+    int dev = 0, sms = 148;
+    WMAR_CUDA_CHECK(cudaGetDevice(&dev));
+    WMAR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int splits = split_k > 0 ? split_k : pick_splits((int)N, (int)K, sms);
+    size_t need = (size_t)(N / GEMM_NT) * splits * GEMM_M * GEMM_NT * sizeof(float);
+    if (need > g_ws_bytes) {
+        if (g_ws) cudaFree(g_ws);
+        WMAR_CUDA_CHECK(cudaMalloc(&g_ws, need));
+        g_ws_bytes = need;
+    }
+    if ((size_t)(N / GEMM_NT) > g_counter_n) {
+        if (g_counters) cudaFree(g_counters);
+        WMAR_CUDA_CHECK(cudaMalloc(&g_counters, sizeof(unsigned) * (size_t)(N / GEMM_NT)));
+        WMAR_CUDA_CHECK(cudaMemset(g_counters, 0, sizeof(unsigned) * (size_t)(N / GEMM_NT)));
+        g_counter_n = (size_t)(N / GEMM_NT);
+    }
+    GemmArgs a{};
+    a.X = d_x; a.ldx = (int)K;
+    a.W = d_w; a.bias = d_bias;
+    a.Y = d_y; a.ldy = (int)N;
+    a.N = (int)N; a.K = (int)K; a.splits = splits;
+    a.ws = g_ws; a.counters = g_counters;
+    return launch_skinny_gemm(PRO_NONE, EPI_STORE, a, as_stream(stream));
+}

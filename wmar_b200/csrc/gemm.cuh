@@ -1,0 +1,283 @@
+// Skinny GEMM for the decode step:  Y[16][N] = pro(X)[16][K] . W[N][K]^T (+ bias, epilogue),  fp32 in / fp32 out.
+//
+// Replaces every nn.Linear of the per-token step (mingpt.py:53-60,105-110,142; rar.py:75,79,127-129,173-176,232).
+// The step is HBM-bound on W (each weight is used for only 16 rows), so the kernel is built around streaming W once
+// with as many 16-byte loads in flight as possible and doing the math on the tensor pipe:
+//   * the 16 batch rows are exactly the M of mma.m16n8k8; W rows map to the MMA's n, so W goes HBM -> registers as
+//     B fragments with NO shared-memory staging (one LDG.128 per lane covers two k8 steps of one n8 tile),
+//   * products are 3xTF32 (hi*hi + hi*lo + lo*hi with fp32 accumulation): fp32-faithful results, which the
+//     reference's fp32 (TF32-off) Linear layers require for greedy token parity,
+//   * split-K across CTAs (grid.y) fills all 148 SMs even for N = 1536; partial tiles go to an L2-resident workspace
+//     and the LAST CTA to arrive for a tile reduces them in split order (deterministic) and runs the epilogue,
+//   * LayerNorm / adaLN-modulate are applied to X on the fly (prologue) from per-row statistics that the producing
+//     GEMM's epilogue emitted as (mean, M2) partials per 64-column tile, combined with Chan's formula.
+#pragma once
+#include "common.cuh"
+
+namespace wmar {
+
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_WARPS = GEMM_THREADS / 32;
+constexpr int GEMM_NT = 64;      // W rows (output columns) per CTA = 8 n8 tiles
+constexpr int GEMM_TILES = GEMM_NT / 8;
+constexpr int GEMM_KI = 16;      // k per warp iteration (one LDG.128 per lane per n8 tile)
+constexpr int GEMM_M = 16;       // batch rows
+constexpr int GEMM_RED_LD = 72;  // padded row of the cross-warp reduction buffer
+
+enum GemmPrologue { PRO_NONE = 0, PRO_LN = 1, PRO_ADALN = 2 };
+enum GemmEpilogue { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_GATE_RESID = 3 };
+
+struct GemmArgs {
+    const float *X; int ldx;
+    const float *W;
+    const float *bias;
+    float *Y; int ldy;
+    int N, K, splits;
+    // prologue
+    const float *ln_g, *ln_b;     // may be null for PRO_ADALN without affine (RAR final layer)
+    const float2 *stats_in;       // [n_stat_tiles][16] (mean, M2) of 64-wide column tiles of X
+    int n_stat_tiles;
+    float eps;
+    const float *mod_scale, *mod_shift; int ld_mod;  // adaLN: x*(1+scale[m][k]) + shift[m][k]
+    // epilogue
+    const float *resid; int ld_resid;
+    const float *gate; int ld_gate;
+    float2 *stats_out;            // [N/64][16] or null
+    float *ws;                    // [N/64][splits][16*64]
+    unsigned *counters;           // [N/64], zero-initialised, self-resetting
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    hi = tf32_hi(x);
+    lo = tf32_hi(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Chan et al. pairwise combination of (count, mean, M2)
+__device__ __forceinline__ void chan_combine(float &n, float &mean, float &m2, float nb, float mb, float m2b) {
+    if (nb == 0.f) return;
+    float nn = n + nb;
+    float d = mb - mean;
+    mean = mean + d * (nb / nn);
+    m2 = m2 + m2b + d * d * (n * nb / nn);
+    n = nn;
+}
+
+// Per-row (mean, rstd) of X from the producer's tile partials; result in smem row_stats[16] (x = mean, y = rstd).
+__device__ __forceinline__ void combine_row_stats(const float2 *__restrict__ stats_in, int n_tiles, int K, float eps,
+                                                  float2 *row_stats) {
+    const int tid = threadIdx.x;
+    const int r = tid >> 4, sub = tid & 15;  // 16 threads per row, contiguous lanes
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+    const float w = (float)(K / n_tiles);
+    for (int tl = sub; tl < n_tiles; tl += 16) {
+        float2 s = stats_in[tl * 16 + r];
+        chan_combine(n, mean, m2, w, s.x, s.y);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        float nb = __shfl_xor_sync(0xffffffffu, n, o);
+        float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+        float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+        // fixed combination tree: lower lane index is always the left operand
+        if ((sub & o) == 0) chan_combine(n, mean, m2, nb, mb, m2b);
+        else { float tn = nb, tm = mb, t2 = m2b; chan_combine(tn, tm, t2, n, mean, m2); n = tn; mean = tm; m2 = t2; }
+    }
+    if (sub == 0) row_stats[r] = make_float2(mean, 1.0f / sqrtf(m2 / (float)K + eps));
+}
+
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a) {
+    __shared__ __align__(16) float red[GEMM_WARPS * GEMM_M * GEMM_RED_LD];
+    __shared__ float2 row_stats[GEMM_M];
+    __shared__ int s_is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const int n0 = tile * GEMM_NT;
+    const int KS = a.K / a.splits;
+    const int KW = KS / GEMM_WARPS;
+    const int kw0 = split * KS + warp * KW;
+    const int iters = KW / GEMM_KI;
+
+    // issue the first weight loads before anything else: they do not depend on the producer kernel
+    const float *wbase = a.W + (size_t)(n0 + g) * a.K + kw0 + 4 * t;
+    float4 wcur[GEMM_TILES];
+#pragma unroll
+    for (int j = 0; j < GEMM_TILES; j++) wcur[j] = ldg_stream(wbase + (size_t)(8 * j) * a.K);
+
+    float2 st_g = make_float2(0.f, 1.f), st_g8 = make_float2(0.f, 1.f);
+    if (PRO != PRO_NONE) {
+        combine_row_stats(a.stats_in, a.n_stat_tiles, a.K, a.eps, row_stats);
+        __syncthreads();
+        st_g = row_stats[g];
+        st_g8 = row_stats[g + 8];
+    }
+
+    float acc[GEMM_TILES][4];
+#pragma unroll
+    for (int j = 0; j < GEMM_TILES; j++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[j][c] = 0.f;
+
+    const float *x_g = a.X + (size_t)g * a.ldx + kw0 + 4 * t;
+    const float *x_g8 = a.X + (size_t)(g + 8) * a.ldx + kw0 + 4 * t;
+
+    for (int it = 0; it < iters; it++) {
+        // prefetch next iteration's weights
+        float4 wnext[GEMM_TILES];
+        if (it + 1 < iters) {
+#pragma unroll
+            for (int j = 0; j < GEMM_TILES; j++) wnext[j] = ldg_stream(wbase + (size_t)(8 * j) * a.K + (it + 1) * GEMM_KI);
+        }
+        const int koff = it * GEMM_KI;
+        float4 xa = *reinterpret_cast<const float4 *>(x_g + koff);
+        float4 xb = *reinterpret_cast<const float4 *>(x_g8 + koff);
+        float xs[2][4] = {{xa.x, xa.y, xa.z, xa.w}, {xb.x, xb.y, xb.z, xb.w}};
+        if (PRO != PRO_NONE) {
+            const int k = kw0 + 4 * t + koff;
+            float gm[4] = {1.f, 1.f, 1.f, 1.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
+            if (a.ln_g != nullptr) {
+                float4 g4 = *reinterpret_cast<const float4 *>(a.ln_g + k);
+                float4 b4 = *reinterpret_cast<const float4 *>(a.ln_b + k);
+                gm[0] = g4.x; gm[1] = g4.y; gm[2] = g4.z; gm[3] = g4.w;
+                bt[0] = b4.x; bt[1] = b4.y; bt[2] = b4.z; bt[3] = b4.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                xs[0][e] = (xs[0][e] - st_g.x) * st_g.y * gm[e] + bt[e];
+                xs[1][e] = (xs[1][e] - st_g8.x) * st_g8.y * gm[e] + bt[e];
+            }
+            if (PRO == PRO_ADALN) {
+                float4 sc0 = *reinterpret_cast<const float4 *>(a.mod_scale + (size_t)g * a.ld_mod + k);
+                float4 sh0 = *reinterpret_cast<const float4 *>(a.mod_shift + (size_t)g * a.ld_mod + k);
+                float4 sc1 = *reinterpret_cast<const float4 *>(a.mod_scale + (size_t)(g + 8) * a.ld_mod + k);
+                float4 sh1 = *reinterpret_cast<const float4 *>(a.mod_shift + (size_t)(g + 8) * a.ld_mod + k);
+                float s0[4] = {sc0.x, sc0.y, sc0.z, sc0.w}, h0[4] = {sh0.x, sh0.y, sh0.z, sh0.w};
+                float s1[4] = {sc1.x, sc1.y, sc1.z, sc1.w}, h1[4] = {sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    xs[0][e] = xs[0][e] * (1.f + s0[e]) + h0[e];
+                    xs[1][e] = xs[1][e] * (1.f + s1[e]) + h1[e];
+                }
+            }
+        }
+        uint32_t xh[2][4], xl[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) split_tf32(xs[r][e], xh[r][e], xl[r][e]);
+#pragma unroll
+        for (int j = 0; j < GEMM_TILES; j++) {
+            const float wv[4] = {wcur[j].x, wcur[j].y, wcur[j].z, wcur[j].w};
+            uint32_t wh[4], wl[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) split_tf32(wv[e], wh[e], wl[e]);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int e = 2 * half;
+                // k-slot t <-> element e, k-slot t+4 <-> element e+1 (any bijection works: the sum over k is unordered)
+                mma_tf32(acc[j], xl[0][e], xl[1][e], xl[0][e + 1], xl[1][e + 1], wh[e], wh[e + 1]);
+                mma_tf32(acc[j], xh[0][e], xh[1][e], xh[0][e + 1], xh[1][e + 1], wl[e], wl[e + 1]);
+                mma_tf32(acc[j], xh[0][e], xh[1][e], xh[0][e + 1], xh[1][e + 1], wh[e], wh[e + 1]);
+            }
+        }
+        if (it + 1 < iters) {
+#pragma unroll
+            for (int j = 0; j < GEMM_TILES; j++) wcur[j] = wnext[j];
+        }
+    }
+
+    // ---- cross-warp reduction (fixed order) ----
+    float *myred = red + warp * GEMM_M * GEMM_RED_LD;
+#pragma unroll
+    for (int j = 0; j < GEMM_TILES; j++) {
+        *reinterpret_cast<float2 *>(myred + g * GEMM_RED_LD + 8 * j + 2 * t) = make_float2(acc[j][0], acc[j][1]);
+        *reinterpret_cast<float2 *>(myred + (g + 8) * GEMM_RED_LD + 8 * j + 2 * t) = make_float2(acc[j][2], acc[j][3]);
+    }
+    __syncthreads();
+    const int m = tid >> 4, nn = (tid & 15) * 4;  // each thread owns 4 consecutive columns of one row
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < GEMM_WARPS; w++) {
+        float4 p = *reinterpret_cast<const float4 *>(red + (w * GEMM_M + m) * GEMM_RED_LD + nn);
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+
+    // ---- split-K: last CTA of the tile reduces the partials in split order ----
+    if (a.splits > 1) {
+        float *wst = a.ws + ((size_t)tile * a.splits) * (GEMM_M * GEMM_NT);
+        __stcg(reinterpret_cast<float4 *>(wst + (size_t)split * (GEMM_M * GEMM_NT) + m * GEMM_NT + nn), v);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            unsigned old = atomicAdd(&a.counters[tile], 1u);
+            s_is_last = (old == (unsigned)(a.splits - 1));
+            if (s_is_last) a.counters[tile] = 0u;
+        }
+        __syncthreads();
+        if (!s_is_last) return;
+        __threadfence();
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < a.splits; s++) {
+            float4 p = __ldcg(reinterpret_cast<const float4 *>(wst + (size_t)s * (GEMM_M * GEMM_NT) + m * GEMM_NT + nn));
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+    }
+
+    // ---- epilogue ----
+    const int n = n0 + nn;
+    if (a.bias != nullptr) {
+        float4 b4 = *reinterpret_cast<const float4 *>(a.bias + n);
+        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+    }
+    if (EPI == EPI_GELU) {
+        v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+    }
+    if (EPI == EPI_GATE_RESID) {
+        float4 g4 = *reinterpret_cast<const float4 *>(a.gate + (size_t)m * a.ld_gate + n);
+        v.x *= g4.x; v.y *= g4.y; v.z *= g4.z; v.w *= g4.w;
+    }
+    if (EPI == EPI_RESID || EPI == EPI_GATE_RESID) {
+        float4 r4 = *reinterpret_cast<const float4 *>(a.resid + (size_t)m * a.ld_resid + n);
+        v.x = r4.x + v.x; v.y = r4.y + v.y; v.z = r4.z + v.z; v.w = r4.w + v.w;
+    }
+    *reinterpret_cast<float4 *>(a.Y + (size_t)m * a.ldy + n) = v;
+    if (a.stats_out != nullptr) {
+        // (mean, M2) of this row's 64 columns: 16 consecutive lanes hold 4 values each
+        float s = v.x + v.y + v.z + v.w;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / GEMM_NT);
+        float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+        float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if ((tid & 15) == 0) a.stats_out[tile * GEMM_M + m] = make_float2(mean, q);
+    }
+}
+
+// host-side launcher (graph-capturable)
+int launch_skinny_gemm(int pro, int epi, const GemmArgs &a, cudaStream_t stream);
+// number of K splits that fills the machine for an [N][K] weight
+int pick_splits(int N, int K, int n_sms);
+
+}  // namespace wmar

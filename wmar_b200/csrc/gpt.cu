@@ -1,0 +1,420 @@
+// Taming minGPT decode engine: the whole sample_with_past loop (mingpt.py:326-368) as a replayed CUDA graph of
+// hand-written kernels, no host work per token.
+//
+// Per step (one graph replay):   for each of L layers
+//     qkv   = LN1(x) Wqkv^T + b              skinny GEMM, LayerNorm fused in the prologue      (mingpt.py:69-78,117)
+//     y     = softmax(q K^T / sqrt(hd)) V     decode attention, appends k,v to the cache in place (:80-90)
+//     x    += y Wproj^T + b                   skinny GEMM, residual epilogue + LN statistics     (:93-94,119)
+//     m     = GELU(LN2(x) W1^T + b1)          skinny GEMM, LN prologue, erf-GELU epilogue        (:105-108)
+//     x    += m W2^T + b2                     skinny GEMM, residual epilogue + LN statistics     (:109,120)
+//   logits = LNf(x) Whead^T                   skinny GEMM                                        (:206-207)
+//   id     = sample(logits)                   watermark bias + /T + top-k + top-p + multinomial  (:349-363)
+//   x      = tok_emb[id] + pos_emb[t+1]       embedding for the next step                        (:186-200)
+// KV cache layout in HBM: K,V fp32 [layer][row(16)][head][block_size][head_dim] -- one contiguous stream per
+// (layer,row,head), so the attention kernel reads 2*(t+1)*hd*4 bytes per CTA with fully coalesced 256 B rows.
+#include <vector>
+
+#include "gemm.cuh"
+#include "sample.cuh"
+
+using namespace wmar;
+
+namespace wmar {
+int make_sample_args(const wmar_wm_params *wm, const wmar_sample_params *sp, int V, SampleArgs *out);
+int *device_err_flag();
+}  // namespace wmar
+
+namespace {
+
+// Per-call parameters read by the kernels of the (pre-captured) step graph.
+struct CallParams {
+    SampleArgs sa;
+    const int64_t *cond;
+    const float *noise;   // [steps][B][V] or null
+    int64_t *out_codes;   // [B][steps]
+    float *out_logits;    // [steps][B][V] or null
+    int B, steps;
+};
+
+struct Layer {
+    const float *ln1_g, *ln1_b, *wqkv, *bqkv, *wproj, *bproj, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2;
+};
+
+}  // namespace
+
+struct wmar_gpt {
+    wmar_gpt_config cfg;
+    int n_sms;
+    const float *tok_emb, *pos_emb, *lnf_g, *lnf_b, *head;
+    std::vector<Layer> layers;
+    // device scratch
+    float *x, *qkv, *y, *hbuf, *logits, *kcache, *vcache, *ws;
+    float2 *stats;
+    unsigned *counters;
+    int64_t *seq;      // [16][block_size + 1]: conditioning token then the generated ids
+    int *step;         // device step counter
+    CallParams *d_call;
+    CallParams *h_call;  // pinned staging
+    cudaEvent_t call_done;
+    bool call_pending;
+    // cached step graph
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    size_t graph_smem;
+    int graph_B;
+    int splits_qkv, splits_proj, splits_fc1, splits_fc2, splits_head;
+    int launches_per_step;
+};
+
+namespace {
+
+constexpr int ATT_THREADS = 256;
+
+// seq[b][0] = cond[b], step = 0
+__global__ void init_call_kernel(const CallParams *cp, int64_t *seq, int seq_ld, int *step) {
+    const int b = threadIdx.x;
+    if (b < cp->B) seq[(size_t)b * seq_ld] = cp->cond[b];
+    if (b == 0) *step = 0;
+}
+
+// x[b] = tok_emb[seq[b][t]] + pos_emb[t]  (t = *step), plus (mean, M2) partials per 64-column tile; rows >= B are zero
+__global__ void __launch_bounds__(256) embed_kernel(const CallParams *cp, const int64_t *seq, int seq_ld,
+                                                    const int *step, const float *__restrict__ tok_emb,
+                                                    const float *__restrict__ pos_emb, int d, int block_size, int V,
+                                                    float *__restrict__ x, float2 *__restrict__ stats) {
+    const int b = blockIdx.x, t = *step;
+    if (t >= block_size) return;  // after the last token there is no next position
+    const bool valid = b < cp->B;
+    long long id = valid ? seq[(size_t)b * seq_ld + t] : 0;
+    if (id < 0 || id >= V) id = 0;
+    const int lane16 = threadIdx.x & 15;
+    for (int c0 = (threadIdx.x >> 4) * 64; c0 < d; c0 += (blockDim.x >> 4) * 64) {
+        // 16 lanes own one 64-column tile
+        const int c = c0 + lane16 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            float4 e = *reinterpret_cast<const float4 *>(tok_emb + (size_t)id * d + c);
+            float4 p = *reinterpret_cast<const float4 *>(pos_emb + (size_t)t * d + c);
+            v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+        }
+        *reinterpret_cast<float4 *>(x + (size_t)b * d + c) = v;
+        float s = v.x + v.y + v.z + v.w;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / 64.0f);
+        float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+        float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if (lane16 == 0) stats[(c0 / 64) * 16 + b] = make_float2(mean, q);
+    }
+}
+
+// One CTA per (head, row).  Appends this step's k,v to the cache and attends over keys 0..t.
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const float *__restrict__ qkv, int d, int H, int T,
+                                                                  float *__restrict__ kcache, float *__restrict__ vcache,
+                                                                  int layer, const int *step, float *__restrict__ y) {
+    static_assert(HD == 64, "Taming head_dim");
+    __shared__ float sc[1024];                      // scores / probabilities (T <= 1024)
+    __shared__ __align__(16) float part[ATT_THREADS / 16][HD];
+    __shared__ float red[ATT_THREADS / 32];
+    const int h = blockIdx.x, b = blockIdx.y, t = *step;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = tid & 15, grp = tid >> 4;       // 16 lanes per key, ATT_THREADS/16 keys in flight
+    constexpr int GROUPS = ATT_THREADS / 16;
+    const float *q = qkv + (size_t)b * 3 * d + h * HD;
+    const float *kn = q + d, *vn = q + 2 * d;
+    const size_t base = (((size_t)layer * 16 + b) * H + h) * (size_t)T * HD;
+    float *K = kcache + base, *Vc = vcache + base;
+    if (tid < 16) *reinterpret_cast<float4 *>(K + (size_t)t * HD + 4 * tid) = *reinterpret_cast<const float4 *>(kn + 4 * tid);
+    else if (tid < 32) *reinterpret_cast<float4 *>(Vc + (size_t)t * HD + 4 * (tid - 16)) = *reinterpret_cast<const float4 *>(vn + 4 * (tid - 16));
+    __syncthreads();
+    const float4 q4 = *reinterpret_cast<const float4 *>(q + 4 * sub);
+    const float scale = 1.0f / sqrtf((float)HD);
+    const int nk = t + 1;
+    for (int j0 = 0; j0 < nk; j0 += GROUPS) {
+        const int j = j0 + grp;
+        float s = 0.f;
+        if (j < nk) {
+            float4 k4 = *reinterpret_cast<const float4 *>(K + (size_t)j * HD + 4 * sub);
+            s = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (j < nk && sub == 0) sc[j] = s * scale;
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int j = tid; j < nk; j += ATT_THREADS) m = fmaxf(m, sc[j]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < ATT_THREADS / 32; w++) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < nk; j += ATT_THREADS) {
+        float e = expf(sc[j] - m);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < ATT_THREADS / 32; w++) sum += red[w];
+    const float inv = 1.0f / sum;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = grp; j < nk; j += GROUPS) {
+        const float p = sc[j] * inv;
+        float4 v4 = *reinterpret_cast<const float4 *>(Vc + (size_t)j * HD + 4 * sub);
+        acc.x += p * v4.x; acc.y += p * v4.y; acc.z += p * v4.z; acc.w += p * v4.w;
+    }
+    *reinterpret_cast<float4 *>(&part[grp][4 * sub]) = acc;
+    __syncthreads();
+    if (tid < HD) {
+        float o = 0.f;
+#pragma unroll
+        for (int gI = 0; gI < GROUPS; gI++) o += part[gI][tid];
+        y[(size_t)b * d + h * HD + tid] = o;
+    }
+}
+
+// lm_head epilogue: watermark + sampler for row b; writes the id into seq / out_codes and (optionally) the raw logits
+__global__ void __launch_bounds__(SAMPLE_THREADS, 1) gpt_sample_kernel(const CallParams *cp, const float *__restrict__ logits,
+                                                                        int64_t *seq, int seq_ld, const int *step, int *err) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int b = blockIdx.x, t = *step;
+    const SampleArgs a = cp->sa;
+    const float *row = logits + (size_t)b * a.V;
+    if (cp->out_logits != nullptr) {
+        float *dst = cp->out_logits + ((size_t)t * cp->B + b) * a.V;
+        for (int v = threadIdx.x; v < a.V; v += SAMPLE_THREADS) dst[v] = row[v];
+    }
+    const float *noise = cp->noise ? cp->noise + ((size_t)t * cp->B + b) * a.V : nullptr;
+    // past_ids of the reference = [cond, ids...] (mingpt.py:328,350), length t + 1
+    int id = sample_row(a, row, seq + (size_t)b * seq_ld, (long long)t + 1, noise,
+                        ((unsigned long long)t << 32) | (unsigned)b, err, smem_raw);
+    if (threadIdx.x == 0) {
+        seq[(size_t)b * seq_ld + t + 1] = id;
+        cp->out_codes[(size_t)b * cp->steps + t] = id;
+    }
+}
+
+__global__ void advance_step_kernel(int *step) { *step += 1; }
+
+int free_graph(wmar_gpt *g) {
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    g->exec = nullptr;
+    g->graph = nullptr;
+    return 0;
+}
+
+// Enqueue the kernels of one decode step on `s` (used both under stream capture and for direct launches).
+int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
+    const wmar_gpt_config &c = g->cfg;
+    const int d = c.n_embd, H = c.n_head, V = c.vocab_size;
+    const int stat_tiles = d / 64;
+    int rc;
+    int launches = 0;
+    for (int l = 0; l < c.n_layer; l++) {
+        const Layer &L = g->layers[l];
+        GemmArgs a{};
+        a.ws = g->ws; a.counters = g->counters; a.eps = 1e-5f;
+        // qkv = LN1(x) Wqkv^T + b
+        a.X = g->x; a.ldx = d; a.W = L.wqkv; a.bias = L.bqkv; a.Y = g->qkv; a.ldy = 3 * d; a.N = 3 * d; a.K = d;
+        a.splits = g->splits_qkv; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b; a.stats_in = g->stats; a.n_stat_tiles = stat_tiles;
+        if ((rc = launch_skinny_gemm(PRO_LN, EPI_STORE, a, s))) return rc;
+        attn_decode_kernel<64><<<dim3(H, B), ATT_THREADS, 0, s>>>(g->qkv, d, H, c.block_size, g->kcache, g->vcache, l,
+                                                                 g->step, g->y);
+        WMAR_LAUNCH_CHECK();
+        // x += y Wproj^T + b
+        GemmArgs p{};
+        p.ws = g->ws; p.counters = g->counters;
+        p.X = g->y; p.ldx = d; p.W = L.wproj; p.bias = L.bproj; p.Y = g->x; p.ldy = d; p.N = d; p.K = d;
+        p.splits = g->splits_proj; p.resid = g->x; p.ld_resid = d; p.stats_out = g->stats;
+        if ((rc = launch_skinny_gemm(PRO_NONE, EPI_RESID, p, s))) return rc;
+        // m = GELU(LN2(x) W1^T + b1)
+        GemmArgs f{};
+        f.ws = g->ws; f.counters = g->counters; f.eps = 1e-5f;
+        f.X = g->x; f.ldx = d; f.W = L.w1; f.bias = L.b1; f.Y = g->hbuf; f.ldy = 4 * d; f.N = 4 * d; f.K = d;
+        f.splits = g->splits_fc1; f.ln_g = L.ln2_g; f.ln_b = L.ln2_b; f.stats_in = g->stats; f.n_stat_tiles = stat_tiles;
+        if ((rc = launch_skinny_gemm(PRO_LN, EPI_GELU, f, s))) return rc;
+        // x += m W2^T + b2
+        GemmArgs o{};
+        o.ws = g->ws; o.counters = g->counters;
+        o.X = g->hbuf; o.ldx = 4 * d; o.W = L.w2; o.bias = L.b2; o.Y = g->x; o.ldy = d; o.N = d; o.K = 4 * d;
+        o.splits = g->splits_fc2; o.resid = g->x; o.ld_resid = d; o.stats_out = g->stats;
+        if ((rc = launch_skinny_gemm(PRO_NONE, EPI_RESID, o, s))) return rc;
+        launches += 5;
+    }
+    GemmArgs hd{};
+    hd.ws = g->ws; hd.counters = g->counters; hd.eps = 1e-5f;
+    hd.X = g->x; hd.ldx = d; hd.W = g->head; hd.bias = nullptr; hd.Y = g->logits; hd.ldy = V; hd.N = V; hd.K = d;
+    hd.splits = g->splits_head; hd.ln_g = g->lnf_g; hd.ln_b = g->lnf_b; hd.stats_in = g->stats; hd.n_stat_tiles = stat_tiles;
+    if ((rc = launch_skinny_gemm(PRO_LN, EPI_STORE, hd, s))) return rc;
+    int *err = device_err_flag();
+    WMAR_REQUIRE(err != nullptr, "cannot allocate the device error flag");
+    gpt_sample_kernel<<<B, SAMPLE_THREADS, sample_smem, s>>>(g->d_call, g->logits, g->seq, c.block_size + 1, g->step, err);
+    WMAR_LAUNCH_CHECK();
+    advance_step_kernel<<<1, 1, 0, s>>>(g->step);
+    WMAR_LAUNCH_CHECK();
+    embed_kernel<<<16, 256, 0, s>>>(g->d_call, g->seq, c.block_size + 1, g->step, g->tok_emb, g->pos_emb, d, c.block_size,
+                                    V, g->x, g->stats);
+    WMAR_LAUNCH_CHECK();
+    launches += 4;
+    g->launches_per_step = launches;
+    return WMAR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, int n_weights, wmar_gpt **out) {
+    WMAR_REQUIRE(cfg != nullptr && d_weights != nullptr && out != nullptr, "NULL argument");
+    WMAR_REQUIRE(cfg->n_embd % 64 == 0 && cfg->n_embd % cfg->n_head == 0, "n_embd must be a multiple of 64 and of n_head");
+    WMAR_REQUIRE(cfg->n_embd / cfg->n_head == 64, "this engine supports head_dim 64 (Taming)");
+    WMAR_REQUIRE(cfg->n_embd % 128 == 0 && cfg->vocab_size % 64 == 0, "n_embd % 128 == 0 and vocab % 64 == 0 required");
+    WMAR_REQUIRE(cfg->block_size >= 1 && cfg->block_size <= 1024, "block_size must be in [1,1024]");
+    WMAR_REQUIRE(cfg->max_batch >= 1 && cfg->max_batch <= 16, "max_batch must be in [1,16]");
+    WMAR_REQUIRE(n_weights == 2 + 12 * cfg->n_layer + 3, "weight table has the wrong number of entries");
+    for (int i = 0; i < n_weights; i++) WMAR_REQUIRE(d_weights[i] != nullptr, "NULL weight pointer");
+    wmar_gpt *g = new (std::nothrow) wmar_gpt();
+    if (!g) return set_error(WMAR_ERR_NOMEM, "out of host memory%s%s");
+    g->cfg = *cfg;
+    int dev = 0;
+    WMAR_CUDA_CHECK(cudaGetDevice(&dev));
+    WMAR_CUDA_CHECK(cudaDeviceGetAttribute(&g->n_sms, cudaDevAttrMultiProcessorCount, dev));
+    auto W = [&](int i) { return reinterpret_cast<const float *>(d_weights[i]); };
+    g->tok_emb = W(0);
+    g->pos_emb = W(1);
+    g->layers.resize(cfg->n_layer);
+    for (int l = 0; l < cfg->n_layer; l++) {
+        int b = 2 + 12 * l;
+        g->layers[l] = Layer{W(b), W(b + 1), W(b + 2), W(b + 3), W(b + 4), W(b + 5), W(b + 6), W(b + 7), W(b + 8), W(b + 9), W(b + 10), W(b + 11)};
+    }
+    int b = 2 + 12 * cfg->n_layer;
+    g->lnf_g = W(b); g->lnf_b = W(b + 1); g->head = W(b + 2);
+    const int d = cfg->n_embd, V = cfg->vocab_size;
+    g->splits_qkv = pick_splits(3 * d, d, g->n_sms);
+    g->splits_proj = pick_splits(d, d, g->n_sms);
+    g->splits_fc1 = pick_splits(4 * d, d, g->n_sms);
+    g->splits_fc2 = pick_splits(d, 4 * d, g->n_sms);
+    g->splits_head = pick_splits(V, d, g->n_sms);
+    size_t ws_floats = 0;
+    auto upd = [&](int N, int S) { size_t n = (size_t)(N / GEMM_NT) * S * GEMM_M * GEMM_NT; if (n > ws_floats) ws_floats = n; };
+    upd(3 * d, g->splits_qkv); upd(d, g->splits_proj); upd(4 * d, g->splits_fc1); upd(d, g->splits_fc2); upd(V, g->splits_head);
+    const size_t kv_elems = (size_t)cfg->n_layer * 16 * d * cfg->block_size;
+    int max_tiles = (V > 4 * d ? V : 4 * d) / GEMM_NT;
+    WMAR_CUDA_CHECK(cudaMalloc(&g->x, sizeof(float) * 16 * d));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->qkv, sizeof(float) * 16 * 3 * d));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->y, sizeof(float) * 16 * d));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->hbuf, sizeof(float) * 16 * 4 * d));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->logits, sizeof(float) * 16 * V));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->kcache, sizeof(float) * kv_elems));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->vcache, sizeof(float) * kv_elems));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->ws, sizeof(float) * (ws_floats ? ws_floats : 1)));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->stats, sizeof(float2) * (d / 64) * 16));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->counters, sizeof(unsigned) * max_tiles));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->seq, sizeof(int64_t) * 16 * (cfg->block_size + 1)));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->step, sizeof(int)));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->d_call, sizeof(CallParams)));
+    WMAR_CUDA_CHECK(cudaMallocHost(&g->h_call, sizeof(CallParams)));
+    WMAR_CUDA_CHECK(cudaEventCreateWithFlags(&g->call_done, cudaEventDisableTiming));
+    g->call_pending = false;
+    WMAR_CUDA_CHECK(cudaMemset(g->counters, 0, sizeof(unsigned) * max_tiles));
+    WMAR_CUDA_CHECK(cudaMemset(g->x, 0, sizeof(float) * 16 * d));
+    WMAR_CUDA_CHECK(cudaMemset(g->qkv, 0, sizeof(float) * 16 * 3 * d));
+    WMAR_CUDA_CHECK(cudaMemset(g->y, 0, sizeof(float) * 16 * d));
+    WMAR_CUDA_CHECK(cudaMemset(g->hbuf, 0, sizeof(float) * 16 * 4 * d));
+    WMAR_CUDA_CHECK(cudaMemset(g->seq, 0, sizeof(int64_t) * 16 * (cfg->block_size + 1)));
+    WMAR_CUDA_CHECK(cudaMemset(g->stats, 0, sizeof(float2) * (d / 64) * 16));
+    g->graph = nullptr; g->exec = nullptr; g->graph_smem = 0; g->graph_B = 0;
+    g->launches_per_step = 5 * cfg->n_layer + 4;
+    *out = g;
+    return WMAR_OK;
+}
+
+void wmar_gpt_destroy(wmar_gpt *g) {
+    if (!g) return;
+    cudaDeviceSynchronize();
+    free_graph(g);
+    cudaFree(g->x); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->hbuf); cudaFree(g->logits);
+    cudaFree(g->kcache); cudaFree(g->vcache); cudaFree(g->ws); cudaFree(g->stats); cudaFree(g->counters);
+    cudaFree(g->seq); cudaFree(g->step); cudaFree(g->d_call); cudaFreeHost(g->h_call);
+    cudaEventDestroy(g->call_done);
+    delete g;
+}
+
+int wmar_gpt_sample(wmar_gpt *g, const wmar_wm_params *wm, const wmar_sample_params *sp, const int64_t *d_cond,
+                    int64_t B, int64_t steps, const float *d_noise, int64_t *d_out_codes, float *d_out_logits,
+                    void *stream) {
+    WMAR_REQUIRE(g != nullptr && sp != nullptr && d_cond != nullptr && d_out_codes != nullptr, "NULL argument");
+    WMAR_REQUIRE(B >= 1 && B <= g->cfg.max_batch, "batch exceeds max_batch");
+    WMAR_REQUIRE(steps >= 1 && steps <= g->cfg.block_size, "steps must be in [1, block_size]");
+    cudaStream_t s = as_stream(stream);
+    wmar_wm_params wm_local{};
+    wm_local.vocab_size = g->cfg.vocab_size;
+    if (wm != nullptr && wm->d_table != nullptr) wm_local = *wm;
+    SampleArgs sa;
+    int rc = make_sample_args(&wm_local, sp, g->cfg.vocab_size, &sa);
+    if (rc) return rc;
+    const size_t smem = sample_smem_bytes(g->cfg.vocab_size, sa.cand_cap);
+    // the pinned staging struct may still be in flight from the previous call
+    if (g->call_pending) WMAR_CUDA_CHECK(cudaEventSynchronize(g->call_done));
+    g->h_call->sa = sa;
+    g->h_call->cond = d_cond;
+    g->h_call->noise = d_noise;
+    g->h_call->out_codes = d_out_codes;
+    g->h_call->out_logits = d_out_logits;
+    g->h_call->B = (int)B;
+    g->h_call->steps = (int)steps;
+    WMAR_CUDA_CHECK(cudaMemcpyAsync(g->d_call, g->h_call, sizeof(CallParams), cudaMemcpyHostToDevice, s));
+    WMAR_CUDA_CHECK(cudaEventRecord(g->call_done, s));
+    g->call_pending = true;
+
+    if (g->exec == nullptr || g->graph_smem != smem || g->graph_B != (int)B) {
+        free_graph(g);
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(gpt_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaStream_t cs;
+        WMAR_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        WMAR_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_step(g, (int)B, smem, cs);
+        cudaError_t e = cudaStreamEndCapture(cs, &g->graph);
+        cudaStreamDestroy(cs);
+        if (rc) { if (g->graph) cudaGraphDestroy(g->graph); g->graph = nullptr; return rc; }
+        if (e != cudaSuccess) return set_error(WMAR_ERR_CUDA, "cudaStreamEndCapture: %s%s", cudaGetErrorString(e));
+        WMAR_CUDA_CHECK(cudaGraphInstantiate(&g->exec, g->graph, 0));
+        g->graph_smem = smem;
+        g->graph_B = (int)B;
+    }
+    init_call_kernel<<<1, 32, 0, s>>>(g->d_call, g->seq, g->cfg.block_size + 1, g->step);
+    WMAR_LAUNCH_CHECK();
+    embed_kernel<<<16, 256, 0, s>>>(g->d_call, g->seq, g->cfg.block_size + 1, g->step, g->tok_emb, g->pos_emb,
+                                    g->cfg.n_embd, g->cfg.block_size, g->cfg.vocab_size, g->x, g->stats);
+    WMAR_LAUNCH_CHECK();
+    for (int64_t t = 0; t < steps; t++) {
+        WMAR_CUDA_CHECK(cudaGraphLaunch(g->exec, s));
+        g_launches.fetch_add((uint64_t)g->launches_per_step);
+    }
+    return WMAR_OK;
+}
+
+double wmar_gpt_algorithmic_bytes(const wmar_gpt *g, int64_t B, int64_t steps) {
+    if (!g) return 0.0;
+    const double d = g->cfg.n_embd, V = g->cfg.vocab_size, L = g->cfg.n_layer;
+    // dense parameters streamed once per step: per layer 12 d^2 + 13 d, head V d, ln_f 2 d
+    const double P = L * (12.0 * d * d + 13.0 * d) + V * d + 2.0 * d;
+    double kv = 0.0;  // K and V rows read per step: t+1 keys at step t, plus the appended row written
+    for (int64_t t = 0; t < steps; t++) kv += 2.0 * L * d * (double)(t + 1) + 2.0 * L * d;
+    return 4.0 * (P * (double)steps + kv * (double)B);
+}
+
+int wmar_gpt_launches_per_step(const wmar_gpt *g) { return g ? g->launches_per_step : 0; }
+
+}  // extern "C"
