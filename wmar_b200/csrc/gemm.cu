@@ -52,6 +52,10 @@ unsigned *g_counters = nullptr;
 size_t g_ws_bytes = 0, g_counter_n = 0;
 }  // namespace
 
+static int g_probe_mode = 0;
+/* test/probe hook (not part of the product path): 0 = 3xTF32, 1 = 1xTF32, 2 = load-only */
+extern "C" void wmar_debug_set_gemm_mode(int mode) { g_probe_mode = mode; }
+
 extern "C" int wmar_skinny_gemm(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t N,
                                 int64_t K, int split_k, void *stream) {
     WMAR_REQUIRE(d_x && d_w && d_y && N > 0 && K > 0, "bad arguments");
@@ -78,5 +82,12 @@ extern "C" int wmar_skinny_gemm(const float *d_x, const float *d_w, const float 
     a.Y = d_y; a.ldy = (int)N;
     a.N = (int)N; a.K = (int)K; a.splits = splits;
     a.ws = g_ws; a.counters = g_counters;
+    if (g_probe_mode != 0) {
+        dim3 grid((unsigned)(a.N / GEMM_NT), (unsigned)a.splits);
+        if (g_probe_mode == 1) skinny_gemm_kernel<PRO_NONE, EPI_STORE, 1><<<grid, GEMM_THREADS, 0, as_stream(stream)>>>(a);
+        else skinny_gemm_kernel<PRO_NONE, EPI_STORE, 2><<<grid, GEMM_THREADS, 0, as_stream(stream)>>>(a);
+        WMAR_LAUNCH_CHECK();
+        return WMAR_OK;
+    }
     return launch_skinny_gemm(PRO_NONE, EPI_STORE, a, as_stream(stream));
 }

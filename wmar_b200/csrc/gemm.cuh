@@ -104,7 +104,7 @@ __device__ __forceinline__ void combine_row_stats(const float2 *__restrict__ sta
     if (sub == 0) row_stats[r] = make_float2(mean, 1.0f / sqrtf(m2 / (float)K + eps));
 }
 
-template <int PRO, int EPI>
+template <int PRO, int EPI, int MODE = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a) {
     __shared__ __align__(16) float red[GEMM_WARPS * GEMM_M * GEMM_RED_LD];
     __shared__ float2 row_stats[GEMM_M];
@@ -195,9 +195,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
             for (int half = 0; half < 2; half++) {
                 const int e = 2 * half;
                 // k-slot t <-> element e, k-slot t+4 <-> element e+1 (any bijection works: the sum over k is unordered)
-                mma_tf32(acc[j], xl[0][e], xl[1][e], xl[0][e + 1], xl[1][e + 1], wh[e], wh[e + 1]);
-                mma_tf32(acc[j], xh[0][e], xh[1][e], xh[0][e + 1], xh[1][e + 1], wl[e], wl[e + 1]);
-                mma_tf32(acc[j], xh[0][e], xh[1][e], xh[0][e + 1], xh[1][e + 1], wh[e], wh[e + 1]);
+                if (MODE == 0) {
+                    mma_tf32(acc[j], xl[0][e], xl[1][e], xl[0][e + 1], xl[1][e + 1], wh[e], wh[e + 1]);
+                    mma_tf32(acc[j], xh[0][e], xh[1][e], xh[0][e + 1], xh[1][e + 1], wl[e], wl[e + 1]);
+                }
+                if (MODE != 2) mma_tf32(acc[j], xh[0][e], xh[1][e], xh[0][e + 1], xh[1][e + 1], wh[e], wh[e + 1]);
+                else acc[j][e] += __uint_as_float(wh[e]) + __uint_as_float(wh[e + 1]);
             }
         }
         if (it + 1 < iters) {

@@ -327,6 +327,7 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
     WMAR_CUDA_CHECK(cudaMallocHost(&g->h_call, sizeof(CallParams)));
     WMAR_CUDA_CHECK(cudaEventCreateWithFlags(&g->call_done, cudaEventDisableTiming));
     g->call_pending = false;
+    WMAR_REQUIRE(device_err_flag() != nullptr, "cannot allocate the device error flag");  // not allowed under capture
     WMAR_CUDA_CHECK(cudaMemset(g->counters, 0, sizeof(unsigned) * max_tiles));
     WMAR_CUDA_CHECK(cudaMemset(g->x, 0, sizeof(float) * 16 * d));
     WMAR_CUDA_CHECK(cudaMemset(g->qkv, 0, sizeof(float) * 16 * 3 * d));

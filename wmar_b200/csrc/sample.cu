@@ -89,7 +89,7 @@ int make_sample_args(const wmar_wm_params *wm, const wmar_sample_params *sp, int
         if (cap > next_pow2(V)) cap = next_pow2(V);
         a.cand_cap = cap;
     }
-    WMAR_REQUIRE(sample_smem_bytes(V, a.cand_cap) <= 220 * 1024, "vocab too large for the shared-memory sampler");
+    WMAR_REQUIRE(sample_smem_bytes(V, a.cand_cap) <= 227 * 1024, "vocab too large for the shared-memory sampler");
     *out = a;
     return WMAR_OK;
 }

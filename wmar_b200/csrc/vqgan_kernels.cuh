@@ -1,0 +1,421 @@
+// CUDA kernels of the VQGAN tokenizer (Taming / Chameleon and MaskGIT families); NHWC fp32 activations in HBM.
+//   conv_igemm_kernel   3x3 / 1x1 convolution as an implicit GEMM on the tensor pipe (TF32 mma, 1x or 3x split),
+//                       cp.async double-buffered smem tiles, fused bias / residual add / nearest-upsample indexing /
+//                       asymmetric-pad stride-2 / NCHW+clamp output           (model.py:39-76,79-138; vqgan.py:64-73)
+//   gn_partial_kernel + gn_apply_kernel   GroupNorm(32, eps 1e-6) statistics and normalise(+swish)  (model.py:30-36)
+//   attn_block_kernel   single-head spatial attention of AttnBlock                                  (model.py:169-193)
+//   gather / rowsumsq / argmin           codebook lookup and nearest-neighbour                      (quantize.py:272-331)
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"  // split_tf32, mma_tf32
+
+namespace wmar {
+
+constexpr int CV_THREADS = 256;
+constexpr int CV_BM = 128, CV_BN = 64, CV_BK = 32, CV_LD = 36;
+
+struct ConvArgs {
+    const float *in, *w, *bias, *resid;
+    float *out;
+    int B, Hs, Ws, Cin, Ho, Wo, Cout, Cout_pad;
+    int ks, stride, pad, up;
+    int nchw_out, do_clamp;
+    float clamp_lo, clamp_hi;
+    float out_scale, out_shift;  // applied before the clamp when nchw_out (RAR: clamp(0,1) then *2-1 handled by caller)
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+template <int PREC3>
+__global__ void __launch_bounds__(CV_THREADS) conv_igemm_kernel(ConvArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float *As = smem;                               // [2][CV_BM][CV_LD]
+    float *Bs = smem + 2 * CV_BM * CV_LD;           // [2][CV_BN][CV_LD]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int m0 = blockIdx.x * CV_BM, n0 = blockIdx.y * CV_BN;
+    const int Hl = a.up ? a.Hs * 2 : a.Hs, Wl = a.up ? a.Ws * 2 : a.Ws;
+    const int cchunks = a.Cin / CV_BK;
+    const int nchunks = a.ks * a.ks * cchunks;
+
+    // the 4 A rows and 2 B rows this thread copies every chunk
+    int ab[4], aoy[4], aox[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int row = (tid + i * CV_THREADS) >> 3;
+        int m = m0 + row;
+        int b = m / (a.Ho * a.Wo);
+        int r = m - b * (a.Ho * a.Wo);
+        ab[i] = b; aoy[i] = r / a.Wo; aox[i] = r - aoy[i] * a.Wo;
+    }
+    const int seg = tid & 7;
+
+    auto load_chunk = [&](int c, int buf) {
+        const int tap = c / cchunks, ci0 = (c - tap * cchunks) * CV_BK;
+        const int ky = tap / a.ks, kx = tap - ky * a.ks;
+        float *Ab = As + buf * CV_BM * CV_LD, *Bb = Bs + buf * CV_BN * CV_LD;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int row = (tid + i * CV_THREADS) >> 3;
+            int iy = aoy[i] * a.stride + ky - a.pad, ix = aox[i] * a.stride + kx - a.pad;
+            bool valid = iy >= 0 && iy < Hl && ix >= 0 && ix < Wl;
+            int sy = a.up ? iy >> 1 : iy, sx = a.up ? ix >> 1 : ix;
+            const float *src = valid ? a.in + (((size_t)ab[i] * a.Hs + sy) * a.Ws + sx) * a.Cin + ci0 + seg * 4 : a.in;
+            cp_async16(Ab + row * CV_LD + seg * 4, src, valid);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            int row = (tid + i * CV_THREADS) >> 3;
+            const float *src = a.w + ((size_t)(n0 + row) * (a.ks * a.ks) + tap) * a.Cin + ci0 + seg * 4;
+            cp_async16(Bb + row * CV_LD + seg * 4, src, true);
+        }
+        cp_async_commit();
+    };
+
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[i][j][c] = 0.f;
+
+    load_chunk(0, 0);
+    for (int c = 0; c < nchunks; c++) {
+        const int buf = c & 1;
+        if (c + 1 < nchunks) {
+            load_chunk(c + 1, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float *Ab = As + buf * CV_BM * CV_LD + (wm * 32) * CV_LD;
+        const float *Bb = Bs + buf * CV_BN * CV_LD + (wn * 32) * CV_LD;
+#pragma unroll
+        for (int k8 = 0; k8 < CV_BK / 8; k8++) {
+            float af[2][4], bf[4][2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const float *p = Ab + (i * 16 + g) * CV_LD + k8 * 8 + t;
+                af[i][0] = p[0]; af[i][1] = p[8 * CV_LD]; af[i][2] = p[4]; af[i][3] = p[8 * CV_LD + 4];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float *p = Bb + (j * 8 + g) * CV_LD + k8 * 8 + t;
+                bf[j][0] = p[0]; bf[j][1] = p[4];
+            }
+            if (PREC3) {
+                uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) split_tf32(af[i][e], ah[i][e], al[i][e]);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) split_tf32(bf[j][e], bh[j][e], bl[j][e]);
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        mma_tf32(acc[i][j], al[i][0], al[i][1], al[i][2], al[i][3], bh[j][0], bh[j][1]);
+                        mma_tf32(acc[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bl[j][0], bl[j][1]);
+                        mma_tf32(acc[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bh[j][0], bh[j][1]);
+                    }
+            } else {
+                uint32_t ah[2][4], bh[4][2];
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) ah[i][e] = tf32_hi(af[i][e]);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) bh[j][e] = tf32_hi(bf[j][e]);
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        mma_tf32(acc[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bh[j][0], bh[j][1]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int m = m0 + wm * 32 + i * 16 + g + half * 8;
+            const int b = m / (a.Ho * a.Wo);
+            const int r = m - b * (a.Ho * a.Wo);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * t;
+                float v0 = acc[i][j][half * 2 + 0], v1 = acc[i][j][half * 2 + 1];
+                if (a.bias != nullptr) { v0 += a.bias[n]; v1 += a.bias[n + 1]; }
+                if (a.nchw_out) {
+                    const int oy = r / a.Wo, ox = r - oy * a.Wo;
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        float v = e ? v1 : v0;
+                        if (n + e < a.Cout) {
+                            if (a.do_clamp) v = fminf(fmaxf(v, a.clamp_lo), a.clamp_hi);
+                            v = v * a.out_scale + a.out_shift;
+                            a.out[(((size_t)b * a.Cout + n + e) * a.Ho + oy) * a.Wo + ox] = v;
+                        }
+                    }
+                } else if (n + 1 < a.Cout) {
+                    const size_t o = (size_t)m * a.Cout + n;
+                    if (a.resid != nullptr) {
+                        float2 rr = *reinterpret_cast<const float2 *>(a.resid + o);
+                        v0 += rr.x; v1 += rr.y;
+                    }
+                    *reinterpret_cast<float2 *>(a.out + o) = make_float2(v0, v1);
+                } else if (n < a.Cout) {
+                    const size_t o = (size_t)m * a.Cout + n;
+                    if (a.resid != nullptr) v0 += a.resid[o];
+                    a.out[o] = v0;
+                }
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------- GroupNorm(32)
+// Stage 1: per (image, pixel-chunk) partial (sum, sum of squares) per group in fp64.
+constexpr int GN_THREADS = 256;
+__global__ void __launch_bounds__(GN_THREADS) gn_partial_kernel(const float *__restrict__ x, int HW, int C, int nchunk,
+                                                                double2 *__restrict__ partial) {
+    // grid (nchunk, B); thread -> fixed channel quad (C/4 quads), strides over pixels of the chunk
+    __shared__ double2 sh[32][GN_THREADS / 32 + 1];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int quads = C >> 2;
+    const int pix_per_chunk = HW / nchunk;
+    const int cg = C / 32;  // channels per group (4, 8, 16)
+    const float *base = x + ((size_t)b * HW + (size_t)chunk * pix_per_chunk) * C;
+    const int tid = threadIdx.x;
+    // threads are laid out so that a thread always sees the same channel quad: requires GN_THREADS % quads == 0 or
+    // quads % GN_THREADS == 0; C in {128,256,512} -> quads in {32,64,128}
+    const int q = tid % quads, prow = tid / quads, pstride = GN_THREADS / quads;
+    float s = 0.f, ss = 0.f;
+    double ds = 0.0, dss = 0.0;
+    int cnt = 0;
+    for (int p = prow; p < pix_per_chunk; p += pstride) {
+        float4 v = *reinterpret_cast<const float4 *>(base + (size_t)p * C + q * 4);
+        s += v.x + v.y + v.z + v.w;
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        if (++cnt == 64) { ds += s; dss += ss; s = 0.f; ss = 0.f; cnt = 0; }
+    }
+    ds += s; dss += ss;
+    // reduce: group of this quad = (q*4)/cg; several quads and several pixel rows map to one group
+    const int grp = (q * 4) / cg;
+    // shared accumulation in a fixed order: first write per-thread values, then one thread per group sums them
+    __shared__ double2 vals[GN_THREADS];
+    vals[tid] = make_double2(ds, dss);
+    __syncthreads();
+    if (tid < 32) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int i = 0; i < GN_THREADS; i++) {
+            int qi = i % quads;
+            if ((qi * 4) / cg == tid) { a0 += vals[i].x; a1 += vals[i].y; }
+        }
+        partial[((size_t)b * nchunk + chunk) * 32 + tid] = make_double2(a0, a1);
+    }
+    (void)sh; (void)grp;
+}
+
+// Stage 2: y = act((x - mean_g) * rstd_g * gamma_c + beta_c); act = swish (x*sigmoid(x)) or identity.
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float *__restrict__ x, float *__restrict__ y, int HW, int C,
+                                                       int nchunk, const double2 *__restrict__ partial,
+                                                       const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                       float eps, int swish) {
+    __shared__ float s_mean[32], s_rstd[32];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 32) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int c = 0; c < nchunk; c++) {
+            double2 p = partial[((size_t)b * nchunk + c) * 32 + threadIdx.x];
+            a0 += p.x; a1 += p.y;
+        }
+        const double n = (double)HW * (C / 32);
+        const double mean = a0 / n;
+        double var = a1 / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int cg = C / 32;
+    const size_t total4 = (size_t)HW * C / 4;
+    const float *xb = x + (size_t)b * HW * C;
+    float *yb = y + (size_t)b * HW * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)((i * 4) % C);
+        const int grp = c / cg;
+        const float mean = s_mean[grp], rstd = s_rstd[grp];
+        float4 v = *reinterpret_cast<const float4 *>(xb + i * 4);
+        float4 g4 = *reinterpret_cast<const float4 *>(gamma + c);
+        float4 b4 = *reinterpret_cast<const float4 *>(beta + c);
+        float o[4] = {(v.x - mean) * rstd * g4.x + b4.x, (v.y - mean) * rstd * g4.y + b4.y,
+                      (v.z - mean) * rstd * g4.z + b4.z, (v.w - mean) * rstd * g4.w + b4.w};
+        if (swish) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) o[e] = o[e] * (1.0f / (1.0f + expf(-o[e])));
+        }
+        *reinterpret_cast<float4 *>(yb + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- AttnBlock core
+// out[b][i][:] = sum_j softmax_j(q_i . k_j * C^-0.5) v_j ; q,k,v,out NHWC [B][N][C].  grid (N/16, B), 256 threads.
+constexpr int AB_Q = 16;
+__global__ void __launch_bounds__(256) attn_block_kernel(const float *__restrict__ q, const float *__restrict__ k,
+                                                         const float *__restrict__ v, float *__restrict__ out, int N,
+                                                         int C) {
+    extern __shared__ __align__(16) float sm[];
+    float *qs = sm;               // [AB_Q][C]
+    float *ps = sm + AB_Q * C;    // [AB_Q][N]
+    const int b = blockIdx.y, i0 = blockIdx.x * AB_Q, tid = threadIdx.x;
+    const float *qb = q + ((size_t)b * N + i0) * C;
+    for (int i = tid; i < AB_Q * C / 4; i += 256) reinterpret_cast<float4 *>(qs)[i] = reinterpret_cast<const float4 *>(qb)[i];
+    __syncthreads();
+    const float scale = 1.0f / sqrtf((float)C);  // int(c)**(-0.5)
+    for (int j = tid; j < N; j += 256) {
+        const float *kj = k + ((size_t)b * N + j) * C;
+        float acc[AB_Q];
+#pragma unroll
+        for (int i = 0; i < AB_Q; i++) acc[i] = 0.f;
+        for (int c = 0; c < C; c += 4) {
+            float4 k4 = *reinterpret_cast<const float4 *>(kj + c);
+#pragma unroll
+            for (int i = 0; i < AB_Q; i++) {
+                float4 q4 = *reinterpret_cast<const float4 *>(qs + i * C + c);
+                acc[i] += q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < AB_Q; i++) ps[i * N + j] = acc[i] * scale;
+    }
+    __syncthreads();
+    // softmax per query row: 8 warps, 2 rows each
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int i = warp; i < AB_Q; i += 8) {
+        float m = -INFINITY;
+        for (int j = lane; j < N; j += 32) m = fmaxf(m, ps[i * N + j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < N; j += 32) { float e = expf(ps[i * N + j] - m); ps[i * N + j] = e; s += e; }
+        s = warp_sum(s);
+        const float inv = 1.0f / s;
+        for (int j = lane; j < N; j += 32) ps[i * N + j] *= inv;
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+        float acc[AB_Q];
+#pragma unroll
+        for (int i = 0; i < AB_Q; i++) acc[i] = 0.f;
+        for (int j = 0; j < N; j++) {
+            const float vv = v[((size_t)b * N + j) * C + c];
+#pragma unroll
+            for (int i = 0; i < AB_Q; i++) acc[i] += ps[i * N + j] * vv;
+        }
+#pragma unroll
+        for (int i = 0; i < AB_Q; i++) out[((size_t)b * N + i0 + i) * C + c] = acc[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------- small kernels
+// NCHW image (3 channels) -> NHWC with Cpad channels (zeros beyond 3); v = x*scale + shift
+__global__ void nchw_to_nhwc_pad_kernel(const float *__restrict__ img, float *__restrict__ out, int B, int HW, int Cpad,
+                                        float scale, float shift) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)B * HW * Cpad;
+    if (i >= total) return;
+    int c = (int)(i % Cpad);
+    size_t p = i / Cpad;
+    int b = (int)(p / HW);
+    int r = (int)(p - (size_t)b * HW);
+    out[i] = c < 3 ? img[((size_t)b * 3 + c) * HW + r] * scale + shift : 0.f;
+}
+
+// zq[b][p][:] = codebook[codes[b][p]][:]
+__global__ void codebook_gather_kernel(const int64_t *__restrict__ codes, const float *__restrict__ emb, float *__restrict__ out,
+                                       size_t n_tok, int D, int n_e) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tok * (size_t)(D / 4)) return;
+    size_t tok = i / (D / 4);
+    int c4 = (int)(i - tok * (D / 4));
+    long long id = codes[tok];
+    if (id < 0 || id >= n_e) id = 0;
+    reinterpret_cast<float4 *>(out)[i] = reinterpret_cast<const float4 *>(emb + (size_t)id * D)[c4];
+}
+
+// out[r] = sum_c x[r][c]^2   (one warp per row)
+__global__ void row_sumsq_kernel(const float *__restrict__ x, float *__restrict__ out, int rows, int D) {
+    int r = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) { float v = x[(size_t)r * D + c]; s += v * v; }
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s;
+}
+
+// codes[r] = argmin_j (zz[r] + ee[j]) - 2 dots[r][j]   (first index on ties)   quantize.py:281-285
+__global__ void __launch_bounds__(256) vq_argmin_kernel(const float *__restrict__ dots, const float *__restrict__ zz,
+                                                        const float *__restrict__ ee, int64_t *__restrict__ codes, int n_e) {
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float z = zz[r];
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = tid; j < n_e; j += 256) {
+        float d = (z + ee[j]) - 2.0f * dots[(size_t)r * n_e + j];
+        if (d < best) { best = d; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; w++)
+            if (sv[w] < best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+        codes[r] = bi;
+    }
+}
+
+// 2x2 average pool, NHWC
+__global__ void avgpool2_kernel(const float *__restrict__ x, float *__restrict__ y, int B, int Ho, int Wo, int C) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)B * Ho * Wo * (C / 4);
+    if (i >= total) return;
+    int c4 = (int)(i % (C / 4));
+    size_t p = i / (C / 4);
+    int ox = (int)(p % Wo);
+    size_t q = p / Wo;
+    int oy = (int)(q % Ho);
+    int b = (int)(q / Ho);
+    const int Wi = Wo * 2, Hi = Ho * 2;
+    const float4 *src = reinterpret_cast<const float4 *>(x);
+    size_t base = (((size_t)b * Hi + 2 * oy) * Wi + 2 * ox) * (C / 4) + c4;
+    float4 a = src[base], bq = src[base + (C / 4)], c = src[base + (size_t)Wi * (C / 4)], d = src[base + (size_t)Wi * (C / 4) + (C / 4)];
+    reinterpret_cast<float4 *>(y)[i] = make_float4((a.x + bq.x + c.x + d.x) * 0.25f, (a.y + bq.y + c.y + d.y) * 0.25f,
+                                                   (a.z + bq.z + c.z + d.z) * 0.25f, (a.w + bq.w + c.w + d.w) * 0.25f);
+}
+
+}  // namespace wmar
