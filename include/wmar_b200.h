@@ -148,6 +148,35 @@ double wmar_gpt_algorithmic_bytes(const wmar_gpt *g, int64_t B, int64_t steps);
 /* kernels launched per decode step by this engine */
 int wmar_gpt_launches_per_step(const wmar_gpt *g);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * RAR decode engine.  Replaces RAR.generate (deps/rar/modeling/rar.py:408-459) + forward_fn (:319-405) + Block /
+ * Attention / FinalLayer (:56-183) as called by RarARMMWrapper.sample (wmar/models/rar_wrapper.py:89-107): classifier-
+ * free guidance u + (c - u) * guidance_scale over rows (cond | none-cond), watermark on the guided logits, /T, softmax,
+ * multinomial; the whole loop enqueued on `stream`.  Weights fp32, borrowed, in this order:
+ *   [0] cls_token [d]  [1] embeddings.weight [codebook+1+n_classes+1][d]  [2] pos_embed [>= seq+2][d]
+ *   [3] target_aware_pos_embed [>= seq+2][d]  [4] timesteps_embeddings [>= seq+1][d]
+ *   per block l (18 entries, base 5 + 18 l): norm1.weight, norm1.bias, attn.qkv.weight [3d][d], attn.qkv.bias,
+ *     attn.q_norm.weight, attn.q_norm.bias, attn.k_norm.weight, attn.k_norm.bias, attn.proj.weight, attn.proj.bias,
+ *     norm2.weight, norm2.bias, mlp.fc1.weight [mlp][d], mlp.fc1.bias, mlp.fc2.weight [d][mlp], mlp.fc2.bias,
+ *     adaLN_modulation.1.weight [6d][d], adaLN_modulation.1.bias
+ *   then adaln_before_head.adaLN_modulation.1.weight [2d][d], .bias, lm_head.weight [codebook][d], lm_head.bias
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct wmar_rar_config {
+    int codebook_size, n_classes, image_seq_len, n_layer, n_head, hidden, mlp;
+    int max_batch; /* images per sampling call, <= 8 (2B guided rows <= 16) */
+} wmar_rar_config;
+
+typedef struct wmar_rar wmar_rar;
+
+int wmar_rar_create(const wmar_rar_config *cfg, const void *const *d_weights, int n_weights, wmar_rar **out);
+void wmar_rar_destroy(wmar_rar *g);
+/* d_cond int64 [B] ImageNet class ids; d_noise fp32 [steps][B][V] or NULL; d_out_ids int64 [B][steps];
+ * d_out_logits (optional) fp32 [steps][B][V] = the guided logits of every step before the watermark. */
+int wmar_rar_sample(wmar_rar *g, const wmar_wm_params *wm, const wmar_sample_params *sp, const int64_t *d_cond,
+                    int64_t B, int64_t steps, float guidance_scale, const float *d_noise, int64_t *d_out_ids,
+                    float *d_out_logits, void *stream);
+double wmar_rar_algorithmic_bytes(const wmar_rar *g, int64_t B, int64_t steps);
+
 /* A single skinny GEMM (the dominant kernel), exposed for unit tests and the roofline microbenchmark:
  * y[16][N] = x[16][K] . W[N][K]^T + bias, fp32 in/out, 3xTF32 tensor-core products with fp32 accumulation. */
 int wmar_skinny_gemm(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t N, int64_t K,

@@ -1,0 +1,132 @@
+"""GPU parity: the VQGAN tokenizer engine (codes_to_images / images_to_codes) vs the torch-fp32 oracle, which is
+itself pinned to the imported reference modules by tests/test_oracle_models.py + tests/golden/vqgan.npz."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import G
+
+pytestmark = pytest.mark.gpu
+
+# pixel tolerance of north_star: 1e-3 RMS; the 3xTF32 path is held to a much tighter max-abs bound
+RMS_TOL_3X = 1e-4
+MAX_TOL_3X = 5e-4
+RMS_TOL_TF32 = 1e-2   # 1xTF32 == the reference's cuDNN default (allow_tf32=True); compared against fp32 oracle
+
+
+def _taming(cfg_over, seed):
+    from oracle import vqgan as ov
+    from wmar_b200.models.vqgan_engine import TAMING_CFG
+    ocfg = dict(ov.TAMING_CFG, **cfg_over)
+    w = ov.synthetic_taming_vqgan_weights(ocfg, seed=seed)
+    ecfg = dict(TAMING_CFG, ch=ocfg["ch"], ch_mult=ocfg["ch_mult"], resolution=ocfg["resolution"],
+                attn_resolution=(ocfg["attn_resolutions"][0] if ocfg["attn_resolutions"] else 0),
+                z_channels=ocfg["z_channels"], embed_dim=ocfg["embed_dim"], n_embed=ocfg["n_embed"])
+    return ov, ocfg, ecfg, w
+
+
+def _maskgit(cfg_over, seed):
+    from oracle import vqgan as ov
+    from wmar_b200.models.vqgan_engine import MASKGIT_CFG
+    ocfg = dict(ov.MASKGIT_CFG, **cfg_over)
+    w = ov.synthetic_maskgit_weights(ocfg, seed=seed)
+    ecfg = dict(MASKGIT_CFG, ch=ocfg["hidden_channels"], ch_mult=ocfg["channel_mult"], resolution=ocfg["resolution"],
+                z_channels=ocfg["z_channels"], embed_dim=ocfg["z_channels"], n_embed=ocfg["num_embeddings"])
+    return ov, ocfg, ecfg, w
+
+
+def _check_codes(got, want, dist_fn):
+    """bit-exact, except where the oracle's own two candidate distances are within fp32 rounding of each other"""
+    got, want = got.cpu().reshape(-1), want.reshape(-1)
+    bad = torch.nonzero(got != want).flatten()
+    assert bad.numel() <= max(1, got.numel() // 200), f"{bad.numel()} of {got.numel()} codes differ"
+    for i in bad.tolist():
+        dg, dw = dist_fn(i, int(got[i])), dist_fn(i, int(want[i]))
+        assert abs(dg - dw) <= 2e-5 * abs(dw), (i, int(got[i]), int(want[i]), dg, dw)
+
+
+SMALL_T = dict(ch=128, ch_mult=(1, 2), resolution=32, attn_resolutions=(16,), n_embed=1024)
+SMALL_M = dict(hidden_channels=128, channel_mult=(1, 2), resolution=32, num_embeddings=512)
+
+
+@pytest.mark.parametrize("family", ["taming", "maskgit"])
+def test_decode_small_matches_oracle(family):
+    from wmar_b200.models.vqgan_engine import VQGANEngine
+    ov, ocfg, ecfg, w = _taming(SMALL_T, 3) if family == "taming" else _maskgit(SMALL_M, 5)
+    dec = ov.taming_codes_to_images if family == "taming" else ov.rar_codes_to_images
+    gen = torch.Generator().manual_seed(21)
+    codes = torch.randint(0, ecfg["n_embed"], (3, 256), generator=gen)
+    want = dec(codes, w, ocfg)
+    eng = VQGANEngine(w, ecfg, max_batch=4)
+    got = eng.decode(codes.cuda()).cpu()
+    assert got.shape == want.shape
+    err = (got - want)
+    assert err.abs().max().item() <= MAX_TOL_3X, err.abs().max().item()
+    assert err.pow(2).mean().sqrt().item() <= RMS_TOL_3X
+    # batch rows are independent and the call is repeatable
+    again = eng.decode(codes[:1].cuda()).cpu()
+    assert torch.equal(again, got[:1])
+    eng_fast = VQGANEngine(w, ecfg, max_batch=4, precision="tf32")
+    got2 = eng_fast.decode(codes.cuda()).cpu()
+    assert (got2 - want).pow(2).mean().sqrt().item() <= RMS_TOL_TF32
+
+
+@pytest.mark.parametrize("family", ["taming", "maskgit"])
+def test_encode_small_matches_oracle(family):
+    from wmar_b200.models.vqgan_engine import VQGANEngine
+    ov, ocfg, ecfg, w = _taming(SMALL_T, 3) if family == "taming" else _maskgit(SMALL_M, 5)
+    gen = torch.Generator().manual_seed(22)
+    img = torch.rand(3, 3, 32, 32, generator=gen) * 2 - 1
+    if family == "taming":
+        want = ov.taming_images_to_codes(img, w, ocfg)
+        z = ov._conv(ov.taming_encoder(img, w, ocfg), w, "quant_conv", padding=0)
+    else:
+        want = ov.rar_images_to_codes(img, w, ocfg)
+        z = ov.maskgit_encoder((img + 1) / 2, w, ocfg)
+    emb = w["quantize.embedding.weight"].double()
+    zf = z.permute(0, 2, 3, 1).reshape(-1, emb.shape[1]).double()
+    eng = VQGANEngine(w, ecfg, max_batch=4)
+    got = eng.encode(img.cuda())
+    assert got.shape == want.shape and got.dtype == torch.int64
+    _check_codes(got, want, lambda i, j: float(((zf[i] - emb[j]) ** 2).sum()))
+
+
+def test_taming_full_config_roundtrip():
+    """BASELINE config 1 on the GPU: Taming-256 VQGAN at the reference's full shapes, encode and decode vs the oracle,
+    plus the committed golden codes produced by the imported reference modules."""
+    from wmar_b200.models.vqgan_engine import VQGANEngine
+    ov, ocfg, ecfg, w = _taming({}, 3)
+    g = np.load(os.path.join(G, "vqgan.npz"))
+    gen = torch.Generator().manual_seed(11)
+    img = torch.rand(1, 3, 256, 256, generator=gen) * 2 - 1
+    eng = VQGANEngine(w, ecfg, max_batch=2)
+    codes = eng.encode(img.cuda())
+    golden = torch.from_numpy(g["taming_full/codes"]).long()
+    z = ov._conv(ov.taming_encoder(img, w, ocfg), w, "quant_conv", padding=0)
+    emb = w["quantize.embedding.weight"].double()
+    zf = z.permute(0, 2, 3, 1).reshape(-1, emb.shape[1]).double()
+    _check_codes(codes, golden, lambda i, j: float(((zf[i] - emb[j]) ** 2).sum()))
+    rec = eng.decode(golden.cuda()).cpu()
+    want = ov.taming_codes_to_images(golden, w, ocfg)
+    err = rec - want
+    assert err.abs().max().item() <= MAX_TOL_3X, err.abs().max().item()
+    assert err.pow(2).mean().sqrt().item() <= RMS_TOL_3X
+    assert float(rec.abs().max()) <= 1.0
+
+
+def test_decode_encode_full_batch_properties():
+    """Full-size batch (B=16, config 2's tokenizer load): size-independent properties -- per-row independence from the
+    batch composition, determinism, and encode(decode(c)) stability under a second round trip."""
+    from wmar_b200.models.vqgan_engine import VQGANEngine
+    ov, ocfg, ecfg, w = _taming({}, 3)
+    eng = VQGANEngine(w, ecfg, max_batch=16, precision="tf32")
+    gen = torch.Generator().manual_seed(5)
+    codes = torch.randint(0, 16384, (16, 256), generator=gen).cuda()
+    img = eng.decode(codes)
+    assert img.shape == (16, 3, 256, 256) and torch.isfinite(img).all()
+    assert torch.equal(eng.decode(codes[3:5]), img[3:5])
+    c1 = eng.encode(img)
+    assert torch.equal(eng.encode(img[7:9]), c1[7:9])
+    assert c1.min() >= 0 and c1.max() < 16384

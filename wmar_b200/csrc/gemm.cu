@@ -13,7 +13,7 @@ static int launch_t(const GemmArgs &a, cudaStream_t stream) {
 
 int launch_skinny_gemm(int pro, int epi, const GemmArgs &a, cudaStream_t stream) {
     WMAR_REQUIRE(a.N % GEMM_NT == 0, "N must be a multiple of 64");
-    WMAR_REQUIRE(a.splits >= 1 && a.K % (a.splits * GEMM_WARPS * GEMM_KI) == 0, "K must be a multiple of splits*128");
+    WMAR_REQUIRE(a.splits >= 1 && a.K % (a.splits * GEMM_KI) == 0, "K must be a multiple of splits*16");
     WMAR_REQUIRE(a.splits == 1 || (a.ws != nullptr && a.counters != nullptr), "split-K needs a workspace");
     WMAR_REQUIRE(a.ldx % 4 == 0 && a.ldy % 4 == 0, "row strides must be multiples of 4 floats");
 #define WMAR_CASE(P, E) \
@@ -35,7 +35,7 @@ int pick_splits(int N, int K, int n_sms) {
     const int target = 2 * n_sms - 16;  // about one full wave at two CTAs per SM
     int best = 1;
     for (int s = 1; s <= 64; s++) {
-        if (K % (s * GEMM_WARPS * GEMM_KI) != 0) continue;
+        if (K % (s * GEMM_KI) != 0 || K / (s * GEMM_KI) < GEMM_WARPS) continue;
         best = s;
         if (tiles * s >= target) break;
     }
@@ -59,7 +59,7 @@ extern "C" void wmar_debug_set_gemm_mode(int mode) { g_probe_mode = mode; }
 extern "C" int wmar_skinny_gemm(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t N,
                                 int64_t K, int split_k, void *stream) {
     WMAR_REQUIRE(d_x && d_w && d_y && N > 0 && K > 0, "bad arguments");
-    WMAR_REQUIRE(N % GEMM_NT == 0 && K % (GEMM_WARPS * GEMM_KI) == 0, "N % 64 == 0 and K % 128 == 0 required");
+    WMAR_REQUIRE(N % GEMM_NT == 0 && K % GEMM_KI == 0, "N % 64 == 0 and K % 16 == 0 required");
     int dev = 0, sms = 148;
     WMAR_CUDA_CHECK(cudaGetDevice(&dev));
     WMAR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

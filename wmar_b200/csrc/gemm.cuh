@@ -113,16 +113,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
     const int g = lane >> 2, t = lane & 3;
     const int tile = blockIdx.x, split = blockIdx.y;
     const int n0 = tile * GEMM_NT;
+    // K is cut into 16-float chunks; chunk c of this split goes to warp c % 8, so the 8 warps of a CTA sweep each
+    // weight row in 512-byte contiguous strides (any K that is a multiple of 16 * splits works)
     const int KS = a.K / a.splits;
-    const int KW = KS / GEMM_WARPS;
-    const int kw0 = split * KS + warp * KW;
-    const int iters = KW / GEMM_KI;
+    const int chunks = KS / GEMM_KI;
+    const int kw0 = split * KS + warp * GEMM_KI;
+    const int iters = warp < chunks ? (chunks - warp + GEMM_WARPS - 1) / GEMM_WARPS : 0;
+    constexpr int KSTEP = GEMM_WARPS * GEMM_KI;
 
     // issue the first weight loads before anything else: they do not depend on the producer kernel
     const float *wbase = a.W + (size_t)(n0 + g) * a.K + kw0 + 4 * t;
     float4 wcur[GEMM_TILES];
 #pragma unroll
-    for (int j = 0; j < GEMM_TILES; j++) wcur[j] = ldg_stream(wbase + (size_t)(8 * j) * a.K);
+    for (int j = 0; j < GEMM_TILES; j++) wcur[j] = iters > 0 ? ldg_stream(wbase + (size_t)(8 * j) * a.K) : make_float4(0.f, 0.f, 0.f, 0.f);
 
     float2 st_g = make_float2(0.f, 1.f), st_g8 = make_float2(0.f, 1.f);
     if (PRO != PRO_NONE) {
@@ -146,9 +149,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
         float4 wnext[GEMM_TILES];
         if (it + 1 < iters) {
 #pragma unroll
-            for (int j = 0; j < GEMM_TILES; j++) wnext[j] = ldg_stream(wbase + (size_t)(8 * j) * a.K + (it + 1) * GEMM_KI);
+            for (int j = 0; j < GEMM_TILES; j++) wnext[j] = ldg_stream(wbase + (size_t)(8 * j) * a.K + (it + 1) * KSTEP);
         }
-        const int koff = it * GEMM_KI;
+        const int koff = it * KSTEP;
         float4 xa = *reinterpret_cast<const float4 *>(x_g + koff);
         float4 xb = *reinterpret_cast<const float4 *>(x_g8 + koff);
         float xs[2][4] = {{xa.x, xa.y, xa.z, xa.w}, {xb.x, xb.y, xb.z, xb.w}};

@@ -1,0 +1,415 @@
+// VQGAN tokenizer engine: codes_to_images / images_to_codes for the Taming (Chameleon) and MaskGIT (RAR) families.
+// A plan of kernel launches is built once from the config + weight table and replayed per call.
+//   Taming   deps/taming/modules/diffusionmodules/model.py:343-538, models/vqgan.py:64-73, vqvae/quantize.py:272-331,
+//            models/cond_transformer.py:169-192, wmar/models/taming_wrapper.py:79-92
+//   MaskGIT  deps/rar/modeling/modules/maskgit_vqgan.py:54-321, modeling/titok.py:75-85, wmar/models/rar_wrapper.py:109-128
+// Weight table order (all fp32 device pointers; conv weights packed [Cout_pad64][ky][kx][Cin_pad32], biases [Cout_pad64],
+// bias-free convs get a zero bias) -- mirrored by wmar_b200/models/vqgan_pack.py:
+//   [0] codebook [n_e][D]
+//   encoder: conv_in, then per level: per block: ResBlock (+ AttnBlock if Taming and res == attn_resolution),
+//            Taming: downsample.conv when not last level;  mid (Taming: block_1, attn_1, block_2; MaskGIT: nrb blocks);
+//            norm_out, conv_out;  Taming only: quant_conv
+//   decoder: Taming only: post_quant_conv;  conv_in;  mid;  per level (high to low): nrb(+1 for Taming) ResBlocks
+//            (+ AttnBlock), upsample conv when level != 0;  norm_out, conv_out
+//   ResBlock  = norm1.g, norm1.b, conv1.w, conv1.b, norm2.g, norm2.b, conv2.w, conv2.b [, nin_shortcut.w, nin_shortcut.b]
+//   AttnBlock = norm.g, norm.b, q.w, q.b, k.w, k.b, v.w, v.b, proj_out.w, proj_out.b
+#include <vector>
+
+#include "vqgan_kernels.cuh"
+
+using namespace wmar;
+
+namespace {
+
+enum OpKind { OP_CONV, OP_GN, OP_ATTN, OP_POOL };
+
+struct Op {
+    OpKind kind;
+    int src, dst, res;  // buffer indices (res = residual buffer or -1)
+    // conv
+    const float *w, *b;
+    int Hs, Ws, Cin, Ho, Wo, Cout, Cout_pad, ks, stride, pad, up;
+    int final_out;  // decoder conv_out: NCHW + clamp into the caller's image
+    // gn
+    const float *gamma, *beta;
+    int swish, H, W, C;
+    // attn: q,k,v buffers
+    int bq, bk, bv;
+};
+
+struct Cursor {
+    const void *const *tab;
+    int n, pos;
+    const float *next() { return pos < n ? reinterpret_cast<const float *>(tab[pos++]) : (pos++, nullptr); }
+};
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct wmar_vqgan {
+    wmar_vqgan_config cfg;
+    const float *codebook;
+    std::vector<Op> enc, dec;
+    const float *quant_w = nullptr, *quant_b = nullptr;
+    float *buf[6];
+    size_t buf_floats;
+    float *dots, *zz, *ee;
+    double2 *gn_partial;
+    double flops_enc, flops_dec;
+    int enc_out_buf, latent;  // buffer holding the encoder output (pre-quant z), latent side
+};
+
+namespace {
+
+struct Builder {
+    wmar_vqgan *v;
+    Cursor cur;
+    std::vector<Op> *ops;
+    int H, W, C;    // current activation shape
+    int x;          // buffer index of the current activation
+    double flops = 0.0;
+
+    int free_buf(std::initializer_list<int> used) {
+        for (int i = 0; i < 6; i++) {
+            bool u = false;
+            for (int k : used) u |= (k == i);
+            if (!u) return i;
+        }
+        return -1;
+    }
+    void conv(int src, int dst, int res, int cout, int ks, int stride, int pad, int up, bool final_out = false) {
+        Op o{};
+        o.kind = OP_CONV; o.src = src; o.dst = dst; o.res = res;
+        o.w = cur.next(); o.b = cur.next();
+        o.Hs = H; o.Ws = W; o.Cin = round_up(C, 32);
+        const int Hl = up ? H * 2 : H, Wl = up ? W * 2 : W;
+        o.Ho = stride == 2 ? Hl / 2 : Hl;
+        o.Wo = stride == 2 ? Wl / 2 : Wl;
+        o.Cout = cout; o.Cout_pad = round_up(cout, 64);
+        o.ks = ks; o.stride = stride; o.pad = pad; o.up = up; o.final_out = final_out ? 1 : 0;
+        ops->push_back(o);
+        flops += 2.0 * o.Ho * o.Wo * (double)cout * (double)(ks * ks) * (double)C;
+        H = o.Ho; W = o.Wo; C = cout;
+    }
+    void gn(int src, int dst, int swish) {
+        Op o{};
+        o.kind = OP_GN; o.src = src; o.dst = dst; o.res = -1;
+        o.gamma = cur.next(); o.beta = cur.next();
+        o.swish = swish; o.H = H; o.W = W; o.C = C;
+        ops->push_back(o);
+    }
+    // Taming: x + h or nin(x) + h ; MaskGIT: h + x or h + nin(h)
+    void resblock(int cout, bool maskgit) {
+        const int cin = C, h0 = H, w0 = W;
+        int t1 = free_buf({x}), t2 = free_buf({x, t1});
+        gn(x, t1, 1);
+        conv(t1, t2, -1, cout, 3, 1, 1, 0);
+        gn(t2, t1, 1);
+        if (cin == cout) {
+            conv(t1, t2, x, cout, 3, 1, 1, 0);  // conv2 + residual x
+            x = t2;
+        } else if (!maskgit) {
+            int t3 = free_buf({x, t1, t2});
+            conv(t1, t3, -1, cout, 3, 1, 1, 0);            // h = conv2
+            H = h0; W = w0; C = cin;
+            conv(x, t2, t3, cout, 1, 1, 0, 0);             // nin_shortcut(x) + h
+            x = t2;
+        } else {
+            int t3 = free_buf({x, t1, t2});
+            conv(t1, t3, -1, cout, 3, 1, 1, 0);            // h = conv2
+            conv(t3, t2, t3, cout, 1, 1, 0, 0);            // nin_shortcut(h) + h   (maskgit_vqgan.py:87-90)
+            x = t2;
+        }
+    }
+    void attnblock() {
+        int t1 = free_buf({x}), bq = free_buf({x, t1}), bk = free_buf({x, t1, bq}), bv = free_buf({x, t1, bq, bk});
+        gn(x, t1, 0);
+        const int c = C;
+        conv(t1, bq, -1, c, 1, 1, 0, 0);
+        conv(t1, bk, -1, c, 1, 1, 0, 0);
+        conv(t1, bv, -1, c, 1, 1, 0, 0);
+        Op o{};
+        o.kind = OP_ATTN; o.bq = bq; o.bk = bk; o.bv = bv; o.dst = t1; o.H = H; o.W = W; o.C = C;
+        ops->push_back(o);
+        flops += 4.0 * (double)(H * W) * (double)(H * W) * (double)C;
+        conv(t1, bq, x, c, 1, 1, 0, 0);  // proj_out + x
+        x = bq;
+    }
+    void pool() {
+        int t1 = free_buf({x});
+        Op o{};
+        o.kind = OP_POOL; o.src = x; o.dst = t1; o.H = H / 2; o.W = W / 2; o.C = C;
+        ops->push_back(o);
+        H /= 2; W /= 2; x = t1;
+    }
+};
+
+int build_plans(wmar_vqgan *v, const void *const *tab, int n) {
+    const wmar_vqgan_config &c = v->cfg;
+    const bool mg = c.family == 1;
+    Builder b{};
+    b.v = v;
+    b.cur = Cursor{tab, n, 0};
+    v->codebook = b.cur.next();
+    // ---------------- encoder: input = NHWC image padded to 32 channels in buffer 0
+    b.ops = &v->enc;
+    b.H = b.W = c.resolution; b.C = 32; b.x = 0; b.flops = 0.0;
+    {
+        int t = b.free_buf({b.x});
+        b.conv(b.x, t, -1, c.ch, 3, 1, 1, 0);
+        b.flops -= 2.0 * c.resolution * c.resolution * (double)c.ch * 9.0 * 29.0;  // padded input channels are zeros
+        b.x = t;
+    }
+    int res = c.resolution;
+    for (int l = 0; l < c.n_levels; l++) {
+        const int cout = c.ch * c.ch_mult[l];
+        for (int k = 0; k < c.num_res_blocks; k++) {
+            b.resblock(cout, mg);
+            if (!mg && c.attn_resolution > 0 && res == c.attn_resolution) b.attnblock();
+        }
+        if (l != c.n_levels - 1) {
+            if (mg) b.pool();
+            else {
+                int t = b.free_buf({b.x});
+                b.conv(b.x, t, -1, b.C, 3, 2, 0, 0);  // pad (0,1,0,1) + stride 2 (model.py:69-72)
+                b.x = t;
+            }
+            res /= 2;
+        }
+    }
+    if (mg) {
+        for (int k = 0; k < c.num_res_blocks; k++) b.resblock(b.C, true);
+    } else {
+        b.resblock(b.C, false);
+        b.attnblock();
+        b.resblock(b.C, false);
+    }
+    {
+        int t1 = b.free_buf({b.x}), t2 = b.free_buf({b.x, t1});
+        b.gn(b.x, t1, 1);
+        b.conv(t1, t2, -1, c.z_channels, mg ? 1 : 3, 1, mg ? 0 : 1, 0);
+        b.x = t2;
+        if (!mg) {
+            int t3 = b.free_buf({b.x});
+            b.conv(b.x, t3, -1, c.embed_dim, 1, 1, 0, 0);  // quant_conv
+            b.x = t3;
+        }
+    }
+    v->enc_out_buf = b.x;
+    v->latent = b.H;
+    v->flops_enc = b.flops + 2.0 * (double)(b.H * b.W) * (double)c.n_embed * (double)c.embed_dim;
+    // ---------------- decoder: input = gathered codebook vectors (NHWC) in buffer 0
+    b.ops = &v->dec;
+    b.H = b.W = v->latent; b.C = c.embed_dim; b.x = 0; b.flops = 0.0;
+    if (!mg) {
+        int t = b.free_buf({b.x});
+        b.conv(b.x, t, -1, c.z_channels, 1, 1, 0, 0);  // post_quant_conv
+        b.x = t;
+    }
+    {
+        int t = b.free_buf({b.x});
+        b.conv(b.x, t, -1, c.ch * c.ch_mult[c.n_levels - 1], 3, 1, 1, 0);
+        b.x = t;
+    }
+    if (mg) {
+        for (int k = 0; k < c.num_res_blocks; k++) b.resblock(b.C, true);
+    } else {
+        b.resblock(b.C, false);
+        b.attnblock();
+        b.resblock(b.C, false);
+    }
+    res = v->latent;
+    for (int l = c.n_levels - 1; l >= 0; l--) {
+        const int cout = c.ch * c.ch_mult[l];
+        const int nblk = mg ? c.num_res_blocks : c.num_res_blocks + 1;
+        for (int k = 0; k < nblk; k++) {
+            b.resblock(cout, mg);
+            if (!mg && c.attn_resolution > 0 && res == c.attn_resolution) b.attnblock();
+        }
+        if (l != 0) {
+            int t = b.free_buf({b.x});
+            b.conv(b.x, t, -1, b.C, 3, 1, 1, 1);  // nearest x2 folded into the conv's input indexing
+            b.x = t;
+            res *= 2;
+        }
+    }
+    {
+        int t1 = b.free_buf({b.x});
+        b.gn(b.x, t1, 1);
+        b.conv(t1, -1, -1, 3, 3, 1, 1, 0, true);
+    }
+    v->flops_dec = b.flops;
+    WMAR_REQUIRE(b.cur.pos == n, "weight table length does not match the architecture");
+    return WMAR_OK;
+}
+
+int run_conv(const wmar_vqgan *v, const Op &o, int B, float *final_out, cudaStream_t s) {
+    ConvArgs a{};
+    a.in = v->buf[o.src]; a.w = o.w; a.bias = o.b;
+    a.resid = o.res >= 0 ? v->buf[o.res] : nullptr;
+    a.out = o.final_out ? final_out : v->buf[o.dst];
+    a.B = B; a.Hs = o.Hs; a.Ws = o.Ws; a.Cin = o.Cin; a.Ho = o.Ho; a.Wo = o.Wo; a.Cout = o.Cout; a.Cout_pad = o.Cout_pad;
+    a.ks = o.ks; a.stride = o.stride; a.pad = o.pad; a.up = o.up;
+    a.out_scale = 1.f; a.out_shift = 0.f;
+    if (o.final_out) {
+        a.nchw_out = 1; a.do_clamp = 1;
+        if (v->cfg.family == 1) { a.clamp_lo = 0.f; a.clamp_hi = 1.f; a.out_scale = 2.f; a.out_shift = -1.f; }
+        else { a.clamp_lo = -1.f; a.clamp_hi = 1.f; }
+    }
+    const long long M = (long long)B * o.Ho * o.Wo;
+    WMAR_REQUIRE(M % CV_BM == 0, "B*Ho*Wo must be a multiple of 128");
+    dim3 grid((unsigned)(M / CV_BM), (unsigned)(o.Cout_pad / CV_BN));
+    const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
+    if (v->cfg.precision == 0) conv_igemm_kernel<1><<<grid, CV_THREADS, smem, s>>>(a);
+    else conv_igemm_kernel<0><<<grid, CV_THREADS, smem, s>>>(a);
+    WMAR_LAUNCH_CHECK();
+    return WMAR_OK;
+}
+
+int gn_chunks(int HW, int C) {
+    int n = 1;
+    while (n < 64 && (long long)HW * C / (n * 2) >= 16384 && (HW / (n * 2)) >= 1) n *= 2;
+    return n;
+}
+
+int run_ops(const wmar_vqgan *v, const std::vector<Op> &ops, int B, float *final_out, cudaStream_t s) {
+    int rc;
+    for (const Op &o : ops) {
+        switch (o.kind) {
+            case OP_CONV:
+                if ((rc = run_conv(v, o, B, final_out, s))) return rc;
+                break;
+            case OP_GN: {
+                const int HW = o.H * o.W, nchunk = gn_chunks(HW, o.C);
+                gn_partial_kernel<<<dim3(nchunk, B), GN_THREADS, 0, s>>>(v->buf[o.src], HW, o.C, nchunk, v->gn_partial);
+                WMAR_LAUNCH_CHECK();
+                long long total4 = (long long)HW * o.C / 4;
+                int gx = (int)((total4 + 255) / 256);
+                if (gx > 1024) gx = 1024;
+                gn_apply_kernel<<<dim3(gx, B), 256, 0, s>>>(v->buf[o.src], v->buf[o.dst], HW, o.C, nchunk, v->gn_partial,
+                                                         o.gamma, o.beta, 1e-6f, o.swish);
+                WMAR_LAUNCH_CHECK();
+                break;
+            }
+            case OP_ATTN: {
+                const int N = o.H * o.W;
+                const size_t smem = sizeof(float) * (size_t)AB_Q * (o.C + N);
+                attn_block_kernel<<<dim3(N / AB_Q, B), 256, smem, s>>>(v->buf[o.bq], v->buf[o.bk], v->buf[o.bv],
+                                                                      v->buf[o.dst], N, o.C);
+                WMAR_LAUNCH_CHECK();
+                break;
+            }
+            case OP_POOL: {
+                size_t total = (size_t)B * o.H * o.W * (o.C / 4);
+                avgpool2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(v->buf[o.src], v->buf[o.dst], B, o.H, o.W, o.C);
+                WMAR_LAUNCH_CHECK();
+                break;
+            }
+        }
+    }
+    return WMAR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights, int n_weights, wmar_vqgan **out) {
+    WMAR_REQUIRE(cfg && d_weights && out, "NULL argument");
+    WMAR_REQUIRE(cfg->family == 0 || cfg->family == 1, "family must be 0 (Taming) or 1 (MaskGIT)");
+    WMAR_REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= 8, "n_levels out of range");
+    WMAR_REQUIRE(cfg->ch % 128 == 0, "base channel count must be a multiple of 128 (GroupNorm kernel: >= 4 channels/group)");
+    WMAR_REQUIRE(cfg->z_channels % 32 == 0 && cfg->embed_dim % 32 == 0 && cfg->n_embed % 64 == 0, "bad latent dims");
+    WMAR_REQUIRE(cfg->max_batch >= 1, "max_batch must be >= 1");
+    WMAR_REQUIRE(cfg->precision == 0 || cfg->precision == 1, "precision must be 0 (3xTF32) or 1 (TF32)");
+    for (int i = 0; i < n_weights; i++) WMAR_REQUIRE(d_weights[i] != nullptr, "NULL weight pointer");
+    wmar_vqgan *v = new (std::nothrow) wmar_vqgan();
+    if (!v) return set_error(WMAR_ERR_NOMEM, "out of host memory%s%s");
+    v->cfg = *cfg;
+    int rc = build_plans(v, d_weights, n_weights);
+    if (rc) { delete v; return rc; }
+    const int R = cfg->resolution;
+    size_t per_img = (size_t)R * R * (size_t)(cfg->ch * cfg->ch_mult[0] > 32 ? cfg->ch * cfg->ch_mult[0] : 32);
+    // the widest activation is at full resolution with ch*ch_mult[0] channels; upsampled tensors at lower levels are
+    // (R/2)^2 * ch*ch_mult[1] <= that as long as ch_mult[1] <= 4*ch_mult[0]
+    for (int l = 0; l < cfg->n_levels; l++) {
+        size_t side = (size_t)R >> l;
+        size_t n = side * side * (size_t)cfg->ch * cfg->ch_mult[l];
+        if (n > per_img) per_img = n;
+        if (l + 1 < cfg->n_levels) {  // decoder: level l+1 channels upsampled to level l resolution
+            size_t n2 = side * side * (size_t)cfg->ch * cfg->ch_mult[l + 1];
+            if (n2 > per_img) per_img = n2;
+        }
+    }
+    v->buf_floats = per_img * (size_t)cfg->max_batch;
+    for (int i = 0; i < 6; i++) WMAR_CUDA_CHECK(cudaMalloc(&v->buf[i], sizeof(float) * v->buf_floats));
+    const size_t tokens = (size_t)cfg->max_batch * v->latent * v->latent;
+    WMAR_CUDA_CHECK(cudaMalloc(&v->dots, sizeof(float) * tokens * cfg->n_embed));
+    WMAR_CUDA_CHECK(cudaMalloc(&v->zz, sizeof(float) * tokens));
+    WMAR_CUDA_CHECK(cudaMalloc(&v->ee, sizeof(float) * cfg->n_embed));
+    WMAR_CUDA_CHECK(cudaMalloc(&v->gn_partial, sizeof(double2) * 64 * 32 * (size_t)cfg->max_batch));
+    row_sumsq_kernel<<<(cfg->n_embed + 7) / 8, 256>>>(v->codebook, v->ee, cfg->n_embed, cfg->embed_dim);
+    WMAR_LAUNCH_CHECK();
+    const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
+    WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WMAR_CUDA_CHECK(cudaFuncSetAttribute(attn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    WMAR_CUDA_CHECK(cudaDeviceSynchronize());
+    *out = v;
+    return WMAR_OK;
+}
+
+void wmar_vqgan_destroy(wmar_vqgan *v) {
+    if (!v) return;
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 6; i++) cudaFree(v->buf[i]);
+    cudaFree(v->dots); cudaFree(v->zz); cudaFree(v->ee); cudaFree(v->gn_partial);
+    delete v;
+}
+
+int wmar_vqgan_decode(wmar_vqgan *v, const int64_t *d_codes, int64_t B, float *d_images, void *stream) {
+    WMAR_REQUIRE(v && d_codes && d_images, "NULL argument");
+    WMAR_REQUIRE(B >= 1 && B <= v->cfg.max_batch, "batch exceeds max_batch");
+    cudaStream_t s = as_stream(stream);
+    const size_t n_tok = (size_t)B * v->latent * v->latent;
+    const int D = v->cfg.embed_dim;
+    size_t n4 = n_tok * (size_t)(D / 4);
+    codebook_gather_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(d_codes, v->codebook, v->buf[0], n_tok, D, v->cfg.n_embed);
+    WMAR_LAUNCH_CHECK();
+    return run_ops(v, v->dec, (int)B, d_images, s);
+}
+
+int wmar_vqgan_encode(wmar_vqgan *v, const float *d_images, int64_t B, int64_t *d_codes, void *stream) {
+    WMAR_REQUIRE(v && d_codes && d_images, "NULL argument");
+    WMAR_REQUIRE(B >= 1 && B <= v->cfg.max_batch, "batch exceeds max_batch");
+    cudaStream_t s = as_stream(stream);
+    const int R = v->cfg.resolution;
+    size_t total = (size_t)B * R * R * 32;
+    // RAR feeds (x+1)/2 to its encoder (rar_wrapper.py:124)
+    const float scale = v->cfg.family == 1 ? 0.5f : 1.f, shift = v->cfg.family == 1 ? 0.5f : 0.f;
+    nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_images, v->buf[0], (int)B, R * R, 32, scale, shift);
+    WMAR_LAUNCH_CHECK();
+    int rc = run_ops(v, v->enc, (int)B, nullptr, s);
+    if (rc) return rc;
+    // nearest codebook entry: dots = z . e^T (always 3xTF32), d = (|z|^2 + |e|^2) - 2 dots, first arg-min
+    const int tokens = (int)B * v->latent * v->latent, D = v->cfg.embed_dim, NE = v->cfg.n_embed;
+    const float *z = v->buf[v->enc_out_buf];
+    row_sumsq_kernel<<<(tokens + 7) / 8, 256, 0, s>>>(z, v->zz, tokens, D);
+    WMAR_LAUNCH_CHECK();
+    ConvArgs a{};
+    a.in = z; a.w = v->codebook; a.bias = nullptr; a.resid = nullptr; a.out = v->dots;
+    a.B = 1; a.Hs = 1; a.Ws = tokens; a.Cin = D; a.Ho = 1; a.Wo = tokens; a.Cout = NE; a.Cout_pad = NE;
+    a.ks = 1; a.stride = 1; a.pad = 0; a.up = 0; a.out_scale = 1.f;
+    WMAR_REQUIRE(tokens % CV_BM == 0, "token count must be a multiple of 128");
+    const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
+    conv_igemm_kernel<1><<<dim3(tokens / CV_BM, NE / CV_BN), CV_THREADS, smem, s>>>(a);
+    WMAR_LAUNCH_CHECK();
+    vq_argmin_kernel<<<tokens, 256, 0, s>>>(v->dots, v->zz, v->ee, d_codes, NE);
+    WMAR_LAUNCH_CHECK();
+    return WMAR_OK;
+}
+
+double wmar_vqgan_flops(const wmar_vqgan *v, int decode) { return v ? (decode ? v->flops_dec : v->flops_enc) : 0.0; }
+
+}  // extern "C"

@@ -18,7 +18,7 @@ class StateModule(nn.Module):
 
     def _insert(self, parts, value):
         if len(parts) == 1:
-            self.register_parameter(parts[0], nn.Parameter(value.detach().clone().float(), requires_grad=False))
+            self.register_parameter(parts[0], nn.Parameter(value.detach().float(), requires_grad=False))
             return
         head = parts[0]
         if head not in self._modules:
