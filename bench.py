@@ -202,6 +202,7 @@ def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     from wmar_b200 import _lib
+    from wmar_b200.distributed import broadcast_state
     from wmar_b200.models import TamingARMMWrapper
     from wmar_b200.models.synthetic import taming_net2net_state
     from wmar_b200.watermarking import create_watermarker_from_string
@@ -218,9 +219,7 @@ def run_ours(args, rank, local_rank, world):
 
     # weights: rank 0 draws them, NCCL broadcast to the replicas (models are replicated, data is sharded)
     state = taming_net2net_state(gpt_cfg, dd, seed=0, device=dev)
-    if world > 1:
-        for k in sorted(state):
-            dist.broadcast(state[k], src=0)
+    broadcast_state(state, src=0)
     model = TamingARMMWrapper(state_dict=state, gpt_cfg=gpt_cfg, dd_cfg=dd, device=dev, max_batch=B,
                               vqgan_precision=args.vqgan_precision, rng=args.rng)
     wm = create_watermarker_from_string(model.get_vq(), model.get_total_vocab_size(), WM_STRING, dev)

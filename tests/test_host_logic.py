@@ -1,0 +1,114 @@
+"""CPU: host-side logic that mirrors the reference (batching / chunking / output tree, generate.py:79-108,179-207),
+the C-ABI exports, and the product path's refusal to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_plan(all_inputs, batch_size, chunk_id, num_chunks):
+    """literal restatement of the loop in generate.py:179-207"""
+    batches = []
+    for i in range(len(all_inputs) // batch_size):
+        batches.append(all_inputs[i * batch_size:(i + 1) * batch_size])
+    if len(all_inputs) % batch_size != 0:
+        batches.append(all_inputs[(len(all_inputs) // batch_size) * batch_size:])
+    base, out = {}, []
+    for batch_idx, batch in enumerate(batches):
+        ci = []
+        for c in batch:
+            if isinstance(c, tuple):
+                c = c[0]
+            if c not in base:
+                base[c] = 0
+            base[c] += 1
+            ci.append(base[c])
+        if batch_idx % num_chunks != chunk_id:
+            continue
+        out.append((batch_idx, batch, ci))
+    return out
+
+
+@pytest.mark.parametrize("n_per,bs,chunks", [(3, 4, 1), (5, 16, 2), (7, 3, 8), (1, 10, 4)])
+def test_plan_batches_matches_reference_loop(n_per, bs, chunks):
+    from wmar_b200.generate import expand_conditionings, plan_batches
+    inputs = expand_conditionings("1,9,232,340,568", n_per)
+    assert len(inputs) == 5 * n_per and inputs[:n_per] == [1] * n_per
+    seen = []
+    for cid in range(chunks):
+        got = plan_batches(inputs, bs, cid, chunks)
+        assert got == _reference_plan(inputs, bs, cid, chunks)
+        seen += [(c, k) for _, b, ci in got for c, k in zip(b, ci)]
+    # every (conditioning, running index) is produced exactly once across the chunks
+    assert sorted(seen) == sorted((c, k + 1) for c in [1, 9, 232, 340, 568] for k in range(n_per))
+
+
+def test_output_tree_names():
+    from wmar_b200.generate import chw_to_uint8, output_paths
+    png, npy, js = output_paths("o", 975, 3, "linear-stratifiedrand-h=1-d=2.0-g=0.25", orig_only=False)
+    assert png == "o/c=975,idx=3/0003_linear-stratifiedrand-h=1-d=2.0-g=0.25_roundtrips_0.png"
+    assert npy.endswith("_roundtrips_0.npy") and js.endswith("_roundtrips_0.json")
+    png, npy, js = output_paths("o", (12, "a cat"), 1, "None", orig_only=True)
+    assert png == "o/images/12:0001.png" and npy == "o/codes/12:0001.npy" and js is None
+    img = np.stack([np.full((2, 2), -1.0), np.zeros((2, 2)), np.full((2, 2), 1.0)])
+    u8 = chw_to_uint8(img)
+    assert u8.shape == (2, 2, 3) and u8[0, 0].tolist() == [0, 128, 255]
+
+
+def test_abi_exports_every_declared_symbol():
+    """include/wmar_b200.h <-> libwmar_b200.so <-> wmar_b200/_lib.py agree (no compute calls: no GPU here)."""
+    from wmar_b200 import _lib, build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "wmar_b200.h")).read()
+    declared = set(re.findall(r"\b(wmar_[a-z0-9_]+)\s*\(", header))
+    declared -= {"wmar_status"}
+    L = ctypes.CDLL(_lib.SO_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
+    _lib.lib()
+    assert _lib.MISSING == []
+    assert _lib.lib().wmar_version() >= 1
+
+
+def test_no_cpu_fallback():
+    from wmar_b200 import _lib
+    from wmar_b200.models import RarARMMWrapper, TamingARMMWrapper
+    from wmar_b200.watermarking import GentimeWatermark, SeedStrategy, SplitStrategy
+    vq = {"alive_ids": torch.arange(8), "dead_ids": torch.arange(8, 16)}
+    with pytest.raises(_lib.WmarError):
+        GentimeWatermark(vq, 16, SeedStrategy.LINEAR, SplitStrategy.RANDOM_STRATIFIED, 1, 2.0, 0.25, device="cpu")
+    with pytest.raises(_lib.WmarError):
+        TamingARMMWrapper(device="cpu")
+    with pytest.raises(_lib.WmarError):
+        RarARMMWrapper(device="cpu")
+
+
+def test_product_never_imports_oracle():
+    """the oracle is test infrastructure: nothing under wmar_b200/ may import or execute it"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "wmar_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+                assert "libwm_oracle" not in src
+
+
+def test_state_module_keeps_reference_keys_and_applies_deltas(tmp_path):
+    from wmar_b200.models.state import StateModule, update_weights
+    flat = {"encoder.conv_in.weight": torch.randn(4, 3, 3, 3), "encoder.down.0.block.0.norm1.bias": torch.randn(4),
+            "quantize.embedding.weight": torch.randn(8, 4)}
+    m = StateModule(flat)
+    assert set(m.state_dict()) == set(flat)
+    assert set(m.encoder.state_dict()) == {"conv_in.weight", "down.0.block.0.norm1.bias"}
+    delta = {"conv_in.weight": torch.ones(4, 3, 3, 3)}
+    p = tmp_path / "enc_delta.pth"
+    torch.save(delta, p)
+    before = m.encoder.conv_in.weight.clone()
+    update_weights(m.encoder, str(p))
+    assert torch.allclose(m.encoder.conv_in.weight, before + 1.0)

@@ -1,0 +1,192 @@
+"""The reference's generation CLI (generate.py:167-345) wired to the B200 engines.
+
+    python -m wmar_b200.generate --outdir out --model taming [--modelpath DIR] --conditioning 1,9,232 \
+        --num_samples_per_conditioning 2 --batch_size 16 --wm_method gentime --wm_seed_strategy linear \
+        --wm_split_strategy stratifiedrand --wm_context_size 1 --wm_delta 2 --wm_gamma 0.25 --orig_only true
+
+Same flags, chunking rule (`batch_idx % num_chunks == chunk_id`, seed + 1000 * chunk_id) and output tree as the
+reference.  Under ``torchrun`` every rank is one chunk (chunk_id = RANK, num_chunks = WORLD_SIZE): independent
+images, no data-path collective.  Without --modelpath the models are seeded random-init at the reference's shapes (no
+checkpoints ship with this repo).  Evaluation under augmentations (generate.py:111-164) is outside the hot path: this
+CLI writes the originals (``--orig_only true`` tree) or, in full mode, the ``roundtrips`` entry with the on-device
+detector's metrics (pvalue, l0) per image.
+"""
+import argparse
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+
+def plan_batches(all_inputs, batch_size, chunk_id=0, num_chunks=1):
+    """generate.py:179-207 -- split into batches (last may be smaller), keep the 1-based running count per
+    conditioning even for batches another chunk owns, return this chunk's [(batch_idx, batch, cond_indices)]."""
+    batches = [all_inputs[i * batch_size:(i + 1) * batch_size] for i in range(len(all_inputs) // batch_size)]
+    if len(all_inputs) % batch_size != 0:
+        batches.append(all_inputs[(len(all_inputs) // batch_size) * batch_size:])
+    counts, mine = {}, []
+    for batch_idx, batch in enumerate(batches):
+        cond_indices = []
+        for c in batch:
+            if isinstance(c, tuple):
+                c = c[0]
+            counts[c] = counts.get(c, 0) + 1
+            cond_indices.append(counts[c])
+        if batch_idx % num_chunks != chunk_id:
+            continue
+        mine.append((batch_idx, batch, cond_indices))
+    return mine
+
+
+def expand_conditionings(conditioning, num_samples_per_conditioning):
+    """generate.py:334-347 -- comma separated ImageNet classes or a prompt file, each repeated n times."""
+    if ".txt" in conditioning:
+        with open(conditioning, "r") as f:
+            conds = [(idx, line.strip()) for idx, line in enumerate(f)]
+    else:
+        conds = [int(c) for c in conditioning.split(",")]
+    return [c for c in conds for _ in range(num_samples_per_conditioning)]
+
+
+def output_paths(outdir, conditioning, cond_index, method, orig_only, transform="roundtrips", param=0):
+    """generate.py:79-108 -- file stems of one image."""
+    if isinstance(conditioning, tuple):
+        conditioning = conditioning[0]
+    if orig_only:
+        return (os.path.join(outdir, "images", f"{conditioning}:{cond_index:04}.png"),
+                os.path.join(outdir, "codes", f"{conditioning}:{cond_index:04}.npy"), None)
+    d = os.path.join(outdir, f"c={conditioning},idx={cond_index}")
+    stem = os.path.join(d, f"{cond_index:04}_{method}_{transform}_{param}")
+    return stem + ".png", stem + ".npy", stem + ".json"
+
+
+def chw_to_uint8(img):
+    """wmar/utils/utils.py chw_to_pillow: [-1,1] CHW float -> HWC uint8"""
+    x = np.clip((np.asarray(img, dtype=np.float32) + 1.0) / 2.0, 0.0, 1.0)
+    return (x.transpose(1, 2, 0) * 255.0).round().astype(np.uint8)
+
+
+def save_png(path, hwc_uint8):
+    try:
+        from PIL import Image
+        Image.fromarray(hwc_uint8).save(path)
+    except ImportError:  # PIL is optional here: fall back to a raw .npy next to the expected name
+        np.save(path + ".npy", hwc_uint8)
+
+
+def get_parser():
+    def str2bool(v):
+        if isinstance(v, bool):
+            return v
+        if v.lower() in ("yes", "true", "t", "y", "1"):
+            return True
+        if v.lower() in ("no", "false", "f", "n", "0"):
+            return False
+        raise argparse.ArgumentTypeError("Boolean value expected.")
+
+    p = argparse.ArgumentParser()
+    p.add_argument("--outdir", type=str)
+    p.add_argument("--model", type=str, choices=["taming", "chameleon7b", "rar"])
+    p.add_argument("--modelpath", type=str, default=None)
+    p.add_argument("--encoder_ft_ckpt", type=str)
+    p.add_argument("--decoder_ft_ckpt", type=str)
+    p.add_argument("--num_samples_per_conditioning", type=int, default=1)
+    p.add_argument("--conditioning", type=str)
+    p.add_argument("--batch_size", type=int, nargs="?", default=10)
+    p.add_argument("--top_k", type=int, nargs="?", default=600)
+    p.add_argument("--temperature", type=float, nargs="?", default=1.0)
+    p.add_argument("--top_p", type=float, nargs="?", default=0.92)
+    p.add_argument("--chunk_id", type=int, nargs="?", default=None)
+    p.add_argument("--num_chunks", type=int, nargs="?", default=None)
+    p.add_argument("--orig_only", type=str2bool, nargs="?", default=False)
+    p.add_argument("--wm_method", type=str, nargs="?", choices=["none", "gentime"], default="none")
+    p.add_argument("--wm_seed_strategy", type=str, nargs="?", choices=["fixed", "linear", "spatial"])
+    p.add_argument("--wm_split_strategy", type=str, nargs="?", choices=["rand", "stratifiedrand", "clustering"])
+    p.add_argument("--wm_context_size", type=int, nargs="?", default=0)
+    p.add_argument("--wm_delta", type=float, nargs="?")
+    p.add_argument("--wm_gamma", type=float, nargs="?", default=0)
+    p.add_argument("--seed", type=int, nargs="?", default=42)
+    return p
+
+
+def main(argv=None):
+    import torch
+    args, _ = get_parser().parse_known_args(argv)
+    assert args.outdir, "Output directory is not set"
+    os.makedirs(args.outdir, exist_ok=True)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    chunk_id = args.chunk_id if args.chunk_id is not None else rank
+    num_chunks = args.num_chunks if args.num_chunks is not None else world
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+
+    seed = args.seed + (1000 * chunk_id)  # generate.py:304
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+
+    from wmar_b200.models import RarARMMWrapper, TamingARMMWrapper
+    from wmar_b200.models.state import update_weights
+    from wmar_b200.watermarking import GentimeWatermark, SeedStrategy, SplitStrategy
+    if args.model == "taming":
+        model = TamingARMMWrapper(args.modelpath, device=device, max_batch=min(16, args.batch_size))
+    elif args.model == "rar":
+        model = RarARMMWrapper(args.modelpath, device=device, max_batch=min(8, args.batch_size))
+    else:
+        raise ValueError(f"Model {args.model} not supported by wmar_b200 yet")
+    patched = False
+    if args.encoder_ft_ckpt not in (None, "none"):
+        update_weights(model.get_image_tokenizer().encoder, args.encoder_ft_ckpt)
+        patched = True
+    if args.decoder_ft_ckpt not in (None, "none"):
+        update_weights(model.get_image_tokenizer().decoder, args.decoder_ft_ckpt)
+        patched = True
+    if patched:
+        model.sync_weights()
+
+    all_inputs = expand_conditionings(args.conditioning, args.num_samples_per_conditioning)
+    if args.model == "rar":
+        assert args.wm_method == "none" or (args.wm_seed_strategy in ["linear", "fixed"]
+                                            and args.wm_split_strategy == "stratifiedrand")
+    watermarker = None
+    if args.wm_method == "gentime":
+        watermarker = GentimeWatermark(model.get_vq(), model.get_total_vocab_size(), SeedStrategy(args.wm_seed_strategy),
+                                       SplitStrategy(args.wm_split_strategy), args.wm_context_size, args.wm_delta,
+                                       args.wm_gamma, model.device)
+    model.set_watermarker(watermarker)
+    gen_params = {"batch_size": args.batch_size, "temperature": args.temperature, "top_k": args.top_k,
+                  "top_p": args.top_p}
+    method = str(watermarker)
+    n_done = 0
+    for batch_idx, batch, cond_indices in plan_batches(all_inputs, args.batch_size, chunk_id, num_chunks):
+        codes = model.sample(batch, gen_params, apply_watermark=watermarker is not None)
+        images = model.codes_to_images(codes)
+        stats = None
+        if not args.orig_only:
+            recodes = model.images_to_codes(images)
+            if watermarker is not None:
+                stats = watermarker.detect(recodes).cpu().numpy()
+            l0 = (recodes != codes).float().mean(dim=1).cpu().numpy()
+        codes_h, images_h = codes.cpu().numpy(), images.cpu().numpy()
+        for i, c in enumerate(batch):
+            png, npy, js = output_paths(args.outdir, c, cond_indices[i], method, args.orig_only)
+            os.makedirs(os.path.dirname(png), exist_ok=True)
+            os.makedirs(os.path.dirname(npy), exist_ok=True)
+            save_png(png, chw_to_uint8(images_h[i]))
+            np.save(npy, codes_h[i])
+            if js is not None:
+                m = {"pvalue": float(stats[i]) if stats is not None else 1.0, "l0": float(l0[i])}
+                with open(js, "w") as f:
+                    json.dump(m, f)
+        n_done += len(batch)
+    print(f"[chunk {chunk_id}/{num_chunks}] wrote {n_done} images to {args.outdir}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
