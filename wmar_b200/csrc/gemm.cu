@@ -1,21 +1,48 @@
 // Launchers for the skinny GEMM + the standalone C-ABI entry used by unit tests and the roofline microbenchmark.
-#include "gemm.cuh"
+#include "gemm_tc.cuh"
 
 namespace wmar {
 
+// 1 = mma.sync kernel (default: measured faster inside the step graph, profiles/), 0 = stand-alone tcgen05 kernel
+// wherever the shape allows it (WMAR_GEMM=tc)
+static int g_gemm_engine = -1;
+static int gemm_engine() {
+    if (g_gemm_engine < 0) {
+        const char *e = getenv("WMAR_GEMM");
+        g_gemm_engine = (e && (e[0] == 't' || e[0] == '0')) ? 0 : 1;
+    }
+    return g_gemm_engine;
+}
+
+// WMAR_PDL=0 turns programmatic dependent launch off (A/B runs)
+static bool v0_pdl() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("WMAR_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
 template <int PRO, int EPI>
 static int launch_t(const GemmArgs &a, cudaStream_t stream) {
-    dim3 grid((unsigned)(a.N / GEMM_NT), (unsigned)a.splits);
-    skinny_gemm_kernel<PRO, EPI><<<grid, GEMM_THREADS, 0, stream>>>(a);
-    WMAR_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(a.N / GEMM_NT), (unsigned)a.splits, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = v0_pdl() ? 1 : 0;
+    WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<PRO, EPI>, a));
+    g_launches.fetch_add(1);
     return WMAR_OK;
 }
 
 int launch_skinny_gemm(int pro, int epi, const GemmArgs &a, cudaStream_t stream) {
+    WMAR_REQUIRE(a.ldx % 4 == 0 && a.ldy % 4 == 0, "row strides must be multiples of 4 floats");
+    if (gemm_engine() == 0 && tc_gemm_eligible(a)) return launch_tc_gemm(pro, epi, a, stream);
     WMAR_REQUIRE(a.N % GEMM_NT == 0, "N must be a multiple of 64");
     WMAR_REQUIRE(a.splits >= 1 && a.K % (a.splits * GEMM_KI) == 0, "K must be a multiple of splits*16");
     WMAR_REQUIRE(a.splits == 1 || (a.ws != nullptr && a.counters != nullptr), "split-K needs a workspace");
-    WMAR_REQUIRE(a.ldx % 4 == 0 && a.ldy % 4 == 0, "row strides must be multiples of 4 floats");
 #define WMAR_CASE(P, E) \
     if (pro == P && epi == E) return launch_t<P, E>(a, stream);
     WMAR_CASE(PRO_NONE, EPI_STORE)
@@ -42,6 +69,14 @@ int pick_splits(int N, int K, int n_sms) {
     return best;
 }
 
+size_t gemm_ws_floats(int N, int K, int splits_v0, int n_sms) {
+    size_t v0 = (size_t)(N / GEMM_NT) * (size_t)splits_v0 * GEMM_M * GEMM_NT;
+    size_t tc = 0;
+    if (N % TC_TILE_N == 0 && K % TC_KC == 0)
+        tc = (size_t)(N / TC_TILE_N) * (size_t)tc_pick_splits(N, K, n_sms) * GEMM_M * TC_TILE_N;
+    return v0 > tc ? v0 : tc;
+}
+
 }  // namespace wmar
 
 using namespace wmar;
@@ -55,6 +90,11 @@ size_t g_ws_bytes = 0, g_counter_n = 0;
 static int g_probe_mode = 0;
 /* test/probe hook (not part of the product path): 0 = 3xTF32, 1 = 1xTF32, 2 = load-only */
 extern "C" void wmar_debug_set_gemm_mode(int mode) { g_probe_mode = mode; }
+/* test hook: 0 = tcgen05 kernel where eligible, 1 = mma.sync kernel everywhere */
+extern "C" void wmar_debug_set_gemm_engine(int engine) { wmar::g_gemm_engine = engine ? 1 : 0; }
+namespace wmar { void tc_gemm_set_pdl(int on); void tc_gemm_set_dbg(int bits); }
+extern "C" void wmar_debug_set_tc_dbg(int bits) { wmar::tc_gemm_set_dbg(bits); }
+extern "C" void wmar_debug_set_pdl(int on) { wmar::tc_gemm_set_pdl(on); }
 
 extern "C" int wmar_skinny_gemm(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t N,
                                 int64_t K, int split_k, void *stream) {
@@ -64,7 +104,7 @@ extern "C" int wmar_skinny_gemm(const float *d_x, const float *d_w, const float 
     WMAR_CUDA_CHECK(cudaGetDevice(&dev));
     WMAR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int splits = split_k > 0 ? split_k : pick_splits((int)N, (int)K, sms);
-    size_t need = (size_t)(N / GEMM_NT) * splits * GEMM_M * GEMM_NT * sizeof(float);
+    size_t need = gemm_ws_floats((int)N, (int)K, splits, sms) * sizeof(float);
     if (need > g_ws_bytes) {
         if (g_ws) cudaFree(g_ws);
         WMAR_CUDA_CHECK(cudaMalloc(&g_ws, need));

@@ -126,6 +126,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
     float4 wcur[GEMM_TILES];
 #pragma unroll
     for (int j = 0; j < GEMM_TILES; j++) wcur[j] = iters > 0 ? ldg_stream(wbase + (size_t)(8 * j) * a.K) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // programmatic dependent launch: the next kernel of the step may start (and issue ITS first weight loads) while this
+    // one runs; everything below reads what the previous kernel produced
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     float2 st_g = make_float2(0.f, 1.f), st_g8 = make_float2(0.f, 1.f);
     if (PRO != PRO_NONE) {
@@ -283,7 +287,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
 
 // host-side launcher (graph-capturable)
 int launch_skinny_gemm(int pro, int epi, const GemmArgs &a, cudaStream_t stream);
-// number of K splits that fills the machine for an [N][K] weight
+// number of K splits that fills the machine for an [N][K] weight (mma.sync kernel)
 int pick_splits(int N, int K, int n_sms);
+// split-K workspace (floats) that covers whichever kernel launch_skinny_gemm picks for this shape
+size_t gemm_ws_floats(int N, int K, int splits_v0, int n_sms);
 
 }  // namespace wmar

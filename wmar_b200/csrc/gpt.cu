@@ -10,11 +10,16 @@
 //   logits = LNf(x) Whead^T                   skinny GEMM                                        (:206-207)
 //   id     = sample(logits)                   watermark bias + /T + top-k + top-p + multinomial  (:349-363)
 //   x      = tok_emb[id] + pos_emb[t+1]       embedding for the next step                        (:186-200)
+// Alternative path (WMAR_STEP=fused, gpt_fused.cuh): per layer  attention block kernel (tcgen05 + TMA + 8-CTA clusters)
+// -> residual reduce -> MLP block kernel -> residual reduce, chained with programmatic dependent launch.  Same token
+// ids; measured 4 % slower than the per-GEMM path on B200 in round 1 (profiles/r01_fused_summary.md), so not the default.
 // KV cache layout in HBM: K,V fp32 [layer][row(16)][head][block_size][head_dim] -- one contiguous stream per
 // (layer,row,head), so the attention kernel reads 2*(t+1)*hd*4 bytes per CTA with fully coalesced 256 B rows.
+#include <algorithm>
 #include <vector>
 
 #include "gemm.cuh"
+#include "gpt_fused.cuh"
 #include "sample.cuh"
 
 using namespace wmar;
@@ -64,6 +69,13 @@ struct wmar_gpt {
     int graph_B;
     int splits_qkv, splits_proj, splits_fc1, splits_fc2, splits_head;
     int launches_per_step;
+    // fused block kernels (gpt_fused.cuh): two kernels + two reductions per layer instead of five GEMMs + attention
+    bool fused;
+    unsigned long long *d_trace;   // probe only (WMAR_STEP_TRACE=<step>): [3][48] stamps: attention + MLP block of layer n_layer/2, attention block of the next layer
+    int trace_step;
+    float *ws2;        // second partial buffer (MLP block)
+    float *hpart;      // K-split partials of the fc1 tiles
+    unsigned *hflag;   // [n_layer][4d/128] arrival counters
 };
 
 namespace {
@@ -119,6 +131,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const float *_
     __shared__ float sc[1024];                      // scores / probabilities (T <= 1024)
     __shared__ __align__(16) float part[ATT_THREADS / 16][HD];
     __shared__ float red[ATT_THREADS / 32];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // qkv comes from the previous kernel
     const int h = blockIdx.x, b = blockIdx.y, t = *step;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = tid & 15, grp = tid >> 4;       // 16 lanes per key, ATT_THREADS/16 keys in flight
@@ -214,6 +228,93 @@ int free_graph(wmar_gpt *g) {
     return 0;
 }
 
+template <int KIND>
+int launch_fused_t(const CUtensorMap &m1, const CUtensorMap &m2, const FusedArgs &a, int groups, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(fused_block_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SM_ALLOC));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(KIND == FB_ATT ? FB_ATT_CS : FB_MLP_CS), (unsigned)groups, 1);
+    cfg.blockDim = dim3(FB_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = FB_SM_ALLOC;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;   // attention block only: the MLP block exchanges through L2
+    attr[1].val.clusterDim.x = FB_ATT_CS;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = KIND == FB_ATT ? 2 : 1;
+    WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_block_kernel<KIND>, m1, m2, a));
+    g_launches.fetch_add(1);
+    return WMAR_OK;
+}
+
+int launch_fused(int kind, const CUtensorMap &m1, const CUtensorMap &m2, const FusedArgs &a, int groups, cudaStream_t s) {
+    return kind == FB_ATT ? launch_fused_t<FB_ATT>(m1, m2, a, groups, s) : launch_fused_t<FB_MLP>(m1, m2, a, groups, s);
+}
+
+int launch_resid_reduce(const float *ws, int P, const float *bias, float *x, float2 *stats, int d, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(d / 32), 1, 1);
+    cfg.blockDim = dim3(RR_THREADS, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, resid_reduce_kernel, ws, P, bias, x, stats, d));
+    g_launches.fetch_add(1);
+    return WMAR_OK;
+}
+
+// The fused block kernels tile this model (and the device can co-schedule their clusters)?
+bool fused_eligible(const wmar_gpt_config &c) {
+    const int d = c.n_embd, H = c.n_head;
+    if (!tc_available() || d % 128 != 0 || d / H != 64 || H % 2 != 0 || c.block_size > FB_ATT_T) return false;
+    const int C1 = d / 32, T2 = d / 128;
+    if (C1 < FB_ATT_CS || (C1 + FB_ATT_CS - 1) / FB_ATT_CS > FB_ATT_B1_MAX) return false;
+    if ((C1 + FB_MLP_CS - 1) / FB_MLP_CS > FB_MLP_B1_MAX || T2 < FB_MLP_CS) return false;
+    int dev = 0, max_smem = 0, n_sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    // the CTAs of an fc1 tile wait for each other: the whole MLP grid (one CTA per SM) must be resident at once
+    if (cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || FB_MLP_CS * (4 * d / 128) > n_sms) return false;
+    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+    if (max_smem < FB_SM_ALLOC) return false;
+    if (cudaFuncSetAttribute(fused_block_kernel<FB_ATT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SM_ALLOC) != cudaSuccess ||
+        cudaFuncSetAttribute(fused_block_kernel<FB_MLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SM_ALLOC) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(FB_ATT_CS, (unsigned)(H / 2), 1);
+    cfg.blockDim = dim3(FB_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = FB_SM_ALLOC;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = FB_ATT_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, fused_block_kernel<FB_ATT>, &cfg) != cudaSuccess || n_clusters < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    if (getenv("WMAR_STEP_TRACE")) {
+        int n_mlp = 0;
+        cfg.gridDim = dim3(FB_MLP_CS, (unsigned)(4 * d / 128), 1);
+        attr[0].val.clusterDim.x = FB_MLP_CS;
+        cudaOccupancyMaxActiveClusters(&n_mlp, fused_block_kernel<FB_MLP>, &cfg);
+        fprintf(stderr, "[wmar] max co-resident clusters: attention (x%d) %d of %d, mlp (x%d) %d of %d\n", FB_ATT_CS, n_clusters,
+                H / 2, FB_MLP_CS, n_mlp, 4 * d / 128);
+    }
+    return true;
+}
+
 // Enqueue the kernels of one decode step on `s` (used both under stream capture and for direct launches).
 int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
     const wmar_gpt_config &c = g->cfg;
@@ -221,7 +322,35 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
     const int stat_tiles = d / 64;
     int rc;
     int launches = 0;
-    for (int l = 0; l < c.n_layer; l++) {
+    if (g->fused) {
+        const int P_att = (H / 2) * 4, P_mlp = 4 * d / 128;
+        for (int l = 0; l < c.n_layer; l++) {
+            const Layer &L = g->layers[l];
+            CUtensorMap mqkv, mproj, mw1, mw2;
+            if ((rc = tc_weight_map(L.wqkv, 3 * d, d, &mqkv))) return rc;
+            if ((rc = tc_weight_map(L.wproj, d, d, &mproj))) return rc;
+            if ((rc = tc_weight_map(L.w1, 4 * d, d, &mw1))) return rc;
+            if ((rc = tc_weight_map(L.w2, d, 4 * d, &mw2))) return rc;
+            FusedArgs a{};
+            a.x = g->x; a.d = d; a.stats_in = g->stats; a.n_stat_tiles = l == 0 ? d / 64 : d / 32; a.eps = 1e-5f;
+            a.ln_g = L.ln1_g; a.ln_b = L.ln1_b; a.bias1 = L.bqkv; a.ws = g->ws; a.C1 = d / 32; a.T2 = d / 128;
+            a.kcache = g->kcache; a.vcache = g->vcache; a.step = g->step; a.H = H; a.T = c.block_size; a.layer = l;
+            { const char *e = getenv("WMAR_FB_DBG"); a.dbg = e ? atoi(e) : 0; }
+            if (g->d_trace && l == c.n_layer / 2) { a.trace = g->d_trace; a.trace_step = g->trace_step; }
+            if (g->d_trace && l == c.n_layer / 2 + 1) { a.trace = g->d_trace + 96; a.trace_step = g->trace_step; }
+            if ((rc = launch_fused(FB_ATT, mqkv, mproj, a, H / 2, s))) return rc;
+            if ((rc = launch_resid_reduce(g->ws, P_att, L.bproj, g->x, g->stats, d, s))) return rc;
+            FusedArgs m{};
+            m.x = g->x; m.d = d; m.stats_in = g->stats; m.n_stat_tiles = d / 32; m.eps = 1e-5f;
+            m.ln_g = L.ln2_g; m.ln_b = L.ln2_b; m.bias1 = L.b1; m.ws = g->ws2; m.C1 = d / 32; m.T2 = d / 128;
+            m.step = g->step; m.dbg = a.dbg; m.hpart = g->hpart; m.hflag = g->hflag + (size_t)l * (4 * d / 128);
+            if (g->d_trace && l == c.n_layer / 2) { m.trace = g->d_trace + 48; m.trace_step = g->trace_step; }
+            if ((rc = launch_fused(FB_MLP, mw1, mw2, m, 4 * d / 128, s))) return rc;
+            if ((rc = launch_resid_reduce(g->ws2, P_mlp, L.b2, g->x, g->stats, d, s))) return rc;
+            launches += 4;
+        }
+    }
+    for (int l = 0; l < (g->fused ? 0 : c.n_layer); l++) {
         const Layer &L = g->layers[l];
         GemmArgs a{};
         a.ws = g->ws; a.counters = g->counters; a.eps = 1e-5f;
@@ -229,9 +358,20 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
         a.X = g->x; a.ldx = d; a.W = L.wqkv; a.bias = L.bqkv; a.Y = g->qkv; a.ldy = 3 * d; a.N = 3 * d; a.K = d;
         a.splits = g->splits_qkv; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b; a.stats_in = g->stats; a.n_stat_tiles = stat_tiles;
         if ((rc = launch_skinny_gemm(PRO_LN, EPI_STORE, a, s))) return rc;
-        attn_decode_kernel<64><<<dim3(H, B), ATT_THREADS, 0, s>>>(g->qkv, d, H, c.block_size, g->kcache, g->vcache, l,
-                                                                 g->step, g->y);
-        WMAR_LAUNCH_CHECK();
+        {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)H, (unsigned)B, 1);
+            cfg.blockDim = dim3(ATT_THREADS, 1, 1);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_decode_kernel<64>, (const float *)g->qkv, d, H, c.block_size, g->kcache,
+                                               g->vcache, l, (const int *)g->step, g->y));
+            g_launches.fetch_add(1);
+        }
         // x += y Wproj^T + b
         GemmArgs p{};
         p.ws = g->ws; p.counters = g->counters;
@@ -255,8 +395,10 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
     GemmArgs hd{};
     hd.ws = g->ws; hd.counters = g->counters; hd.eps = 1e-5f;
     hd.X = g->x; hd.ldx = d; hd.W = g->head; hd.bias = nullptr; hd.Y = g->logits; hd.ldy = V; hd.N = V; hd.K = d;
-    hd.splits = g->splits_head; hd.ln_g = g->lnf_g; hd.ln_b = g->lnf_b; hd.stats_in = g->stats; hd.n_stat_tiles = stat_tiles;
+    hd.splits = g->splits_head; hd.ln_g = g->lnf_g; hd.ln_b = g->lnf_b; hd.stats_in = g->stats;
+    hd.n_stat_tiles = g->fused ? d / 32 : stat_tiles;
     if ((rc = launch_skinny_gemm(PRO_LN, EPI_STORE, hd, s))) return rc;
+    launches += 1;
     int *err = device_err_flag();
     WMAR_REQUIRE(err != nullptr, "cannot allocate the device error flag");
     gpt_sample_kernel<<<B, SAMPLE_THREADS, sample_smem, s>>>(g->d_call, g->logits, g->seq, c.block_size + 1, g->step, err);
@@ -266,7 +408,7 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
     embed_kernel<<<16, 256, 0, s>>>(g->d_call, g->seq, c.block_size + 1, g->step, g->tok_emb, g->pos_emb, d, c.block_size,
                                     V, g->x, g->stats);
     WMAR_LAUNCH_CHECK();
-    launches += 4;
+    launches += 3;
     g->launches_per_step = launches;
     return WMAR_OK;
 }
@@ -307,8 +449,9 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
     g->splits_fc2 = pick_splits(d, 4 * d, g->n_sms);
     g->splits_head = pick_splits(V, d, g->n_sms);
     size_t ws_floats = 0;
-    auto upd = [&](int N, int S) { size_t n = (size_t)(N / GEMM_NT) * S * GEMM_M * GEMM_NT; if (n > ws_floats) ws_floats = n; };
-    upd(3 * d, g->splits_qkv); upd(d, g->splits_proj); upd(4 * d, g->splits_fc1); upd(d, g->splits_fc2); upd(V, g->splits_head);
+    auto upd = [&](int N, int K, int S) { size_t n = gemm_ws_floats(N, K, S, g->n_sms); if (n > ws_floats) ws_floats = n; };
+    upd(3 * d, d, g->splits_qkv); upd(d, d, g->splits_proj); upd(4 * d, d, g->splits_fc1); upd(d, 4 * d, g->splits_fc2);
+    upd(V, d, g->splits_head);
     const size_t kv_elems = (size_t)cfg->n_layer * 16 * d * cfg->block_size;
     int max_tiles = (V > 4 * d ? V : 4 * d) / GEMM_NT;
     WMAR_CUDA_CHECK(cudaMalloc(&g->x, sizeof(float) * 16 * d));
@@ -319,7 +462,7 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
     WMAR_CUDA_CHECK(cudaMalloc(&g->kcache, sizeof(float) * kv_elems));
     WMAR_CUDA_CHECK(cudaMalloc(&g->vcache, sizeof(float) * kv_elems));
     WMAR_CUDA_CHECK(cudaMalloc(&g->ws, sizeof(float) * (ws_floats ? ws_floats : 1)));
-    WMAR_CUDA_CHECK(cudaMalloc(&g->stats, sizeof(float2) * (d / 64) * 16));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->stats, sizeof(float2) * (d / 32) * 16));
     WMAR_CUDA_CHECK(cudaMalloc(&g->counters, sizeof(unsigned) * max_tiles));
     WMAR_CUDA_CHECK(cudaMalloc(&g->seq, sizeof(int64_t) * 16 * (cfg->block_size + 1)));
     WMAR_CUDA_CHECK(cudaMalloc(&g->step, sizeof(int)));
@@ -334,9 +477,40 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
     WMAR_CUDA_CHECK(cudaMemset(g->y, 0, sizeof(float) * 16 * d));
     WMAR_CUDA_CHECK(cudaMemset(g->hbuf, 0, sizeof(float) * 16 * 4 * d));
     WMAR_CUDA_CHECK(cudaMemset(g->seq, 0, sizeof(int64_t) * 16 * (cfg->block_size + 1)));
-    WMAR_CUDA_CHECK(cudaMemset(g->stats, 0, sizeof(float2) * (d / 64) * 16));
+    WMAR_CUDA_CHECK(cudaMemset(g->stats, 0, sizeof(float2) * (d / 32) * 16));
     g->graph = nullptr; g->exec = nullptr; g->graph_smem = 0; g->graph_B = 0;
     g->launches_per_step = 5 * cfg->n_layer + 4;
+    // fused block kernels whenever the model tiles (WMAR_STEP=graph forces the per-GEMM path)
+    g->fused = false; g->ws2 = nullptr; g->hpart = nullptr; g->hflag = nullptr; g->d_trace = nullptr; g->trace_step = -1;
+    {
+        const char *e = getenv("WMAR_STEP_TRACE");
+        if (e) {
+            g->trace_step = atoi(e);
+            WMAR_CUDA_CHECK(cudaMalloc(&g->d_trace, sizeof(unsigned long long) * 144));
+            WMAR_CUDA_CHECK(cudaMemset(g->d_trace, 0, sizeof(unsigned long long) * 144));
+            const unsigned long long big = ~0ull;   // the "min" slots
+            for (int k = 0; k < 3; k++) {
+                WMAR_CUDA_CHECK(cudaMemcpy(g->d_trace + 48 * k + 40, &big, 8, cudaMemcpyHostToDevice));
+                WMAR_CUDA_CHECK(cudaMemcpy(g->d_trace + 48 * k + 42, &big, 8, cudaMemcpyHostToDevice));
+            }
+        }
+    }
+    {
+        const char *e = getenv("WMAR_STEP");
+        const bool want_fused = e && e[0] == 'f';   // default: per-GEMM graph path (measured faster, profiles/r01_*)
+        if (want_fused && fused_eligible(*cfg)) {
+            const size_t P = (size_t)std::max((cfg->n_head / 2) * 4, 4 * d / 128);
+            if (ws_floats < P * 16 * d) {
+                cudaFree(g->ws);
+                WMAR_CUDA_CHECK(cudaMalloc(&g->ws, sizeof(float) * P * 16 * d));
+            }
+            WMAR_CUDA_CHECK(cudaMalloc(&g->ws2, sizeof(float) * P * 16 * d));
+            WMAR_CUDA_CHECK(cudaMalloc(&g->hpart, sizeof(float) * (size_t)(4 * d / 128) * FB_MLP_CS * 16 * 128));
+            WMAR_CUDA_CHECK(cudaMalloc(&g->hflag, sizeof(unsigned) * (size_t)cfg->n_layer * (4 * d / 128)));
+            g->fused = true;
+            g->launches_per_step = 4 * cfg->n_layer + 4;
+        }
+    }
     *out = g;
     return WMAR_OK;
 }
@@ -348,6 +522,7 @@ void wmar_gpt_destroy(wmar_gpt *g) {
     cudaFree(g->x); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->hbuf); cudaFree(g->logits);
     cudaFree(g->kcache); cudaFree(g->vcache); cudaFree(g->ws); cudaFree(g->stats); cudaFree(g->counters);
     cudaFree(g->seq); cudaFree(g->step); cudaFree(g->d_call); cudaFreeHost(g->h_call);
+    cudaFree(g->ws2); cudaFree(g->d_trace); cudaFree(g->hpart); cudaFree(g->hflag);
     cudaEventDestroy(g->call_done);
     delete g;
 }
@@ -394,6 +569,8 @@ int wmar_gpt_sample(wmar_gpt *g, const wmar_wm_params *wm, const wmar_sample_par
         g->graph_smem = smem;
         g->graph_B = (int)B;
     }
+    if (g->fused)
+        WMAR_CUDA_CHECK(cudaMemsetAsync(g->hflag, 0, sizeof(unsigned) * (size_t)g->cfg.n_layer * (4 * g->cfg.n_embd / 128), s));
     init_call_kernel<<<1, 32, 0, s>>>(g->d_call, g->seq, g->cfg.block_size + 1, g->step);
     WMAR_LAUNCH_CHECK();
     embed_kernel<<<16, 256, 0, s>>>(g->d_call, g->seq, g->cfg.block_size + 1, g->step, g->tok_emb, g->pos_emb,
@@ -417,5 +594,13 @@ double wmar_gpt_algorithmic_bytes(const wmar_gpt *g, int64_t B, int64_t steps) {
 }
 
 int wmar_gpt_launches_per_step(const wmar_gpt *g) { return g ? g->launches_per_step : 0; }
+
+/* probe only: copies the [3][48] globaltimer stamps of the traced step to the host */
+int wmar_gpt_debug_trace(const wmar_gpt *g, unsigned long long *out) {
+    WMAR_REQUIRE(g != nullptr && g->d_trace != nullptr && out != nullptr, "tracing is off (WMAR_STEP_TRACE)");
+    WMAR_CUDA_CHECK(cudaDeviceSynchronize());
+    WMAR_CUDA_CHECK(cudaMemcpy(out, g->d_trace, sizeof(unsigned long long) * 144, cudaMemcpyDeviceToHost));
+    return WMAR_OK;
+}
 
 }  // extern "C"

@@ -374,13 +374,13 @@ int wmar_rar_create(const wmar_rar_config *cfg, const void *const *d_weights, in
     g->s_lm = pick_splits(V, d, g->n_sms);
     size_t ws_floats = 1;
     int max_tiles = 1;
-    auto upd = [&](int N, int S) {
-        size_t n = (size_t)(N / GEMM_NT) * S * GEMM_M * GEMM_NT;
+    auto upd = [&](int N, int K, int S) {
+        size_t n = gemm_ws_floats(N, K, S, g->n_sms);
         if (n > ws_floats) ws_floats = n;
         if (N / GEMM_NT > max_tiles) max_tiles = N / GEMM_NT;
     };
-    upd(6 * d, g->s_ada); upd(3 * d, g->s_qkv); upd(d, g->s_proj); upd(mlp, g->s_fc1); upd(d, g->s_fc2);
-    upd(2 * d, g->s_hada); upd(V, g->s_lm);
+    upd(6 * d, d, g->s_ada); upd(3 * d, d, g->s_qkv); upd(d, d, g->s_proj); upd(mlp, d, g->s_fc1); upd(d, mlp, g->s_fc2);
+    upd(2 * d, d, g->s_hada); upd(V, d, g->s_lm);
     const size_t kv_elems = (size_t)cfg->n_layer * 16 * d * g->T;
     WMAR_CUDA_CHECK(cudaMalloc(&g->x, sizeof(float) * 16 * d));
     WMAR_CUDA_CHECK(cudaMalloc(&g->csilu, sizeof(float) * 16 * d));
