@@ -182,6 +182,59 @@ double wmar_rar_algorithmic_bytes(const wmar_rar *g, int64_t B, int64_t steps);
 int wmar_skinny_gemm(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t N, int64_t K,
                      int split_k, void *stream);
 
+/* The same GEMM with bf16 weights (Chameleon / Anole): y = bf16(bf16(x) . W^T), fp32 accumulation, y holds bf16 values. */
+int wmar_skinny_gemm_bf16(const float *d_x, const void *d_w_bf16, float *d_y, int64_t N, int64_t K, int split_k,
+                          void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Chameleon / Anole-7B image-token decode engine.
+ * Replaces, for image generation, ImageDecoder.__init__/__next__ (deps/chameleon/inference/chameleon.py:299-389), the
+ * ChameleonGenerator step (generation.py:68-103), ChameleonModelAdapter (model_adapter.py:51-118, the per-row key
+ * ranges of BlockDiagonalCausalWithOffsetPaddedKeysMask) and Transformer.forward_with_attn_bias
+ * (transformer.py:97-337), with the logits processors of chameleon.py:312-327 (InBatchInstructCFGLogitsProcessor,
+ * the watermark callback, AllowOnlyTokensLogitsProcessor, temperature, top-p) and the
+ * ReplicatedInputTokenSelector(Multinomial | Argmax, n=3) of token_selector.py:26-47 fused behind the output head.
+ * The model is bf16 (matrices as bf16, norm parameters as fp32 holding the bf16 values), weights borrowed, in this order:
+ *   [0] tok_embeddings.weight bf16 [V][d]
+ *   per layer l (10 entries, base 1 + 10 l): attention_norm.weight f32 [d], attention.wqkv.weight bf16 [(H+2Hkv)128][d],
+ *     attention.q_normalization.weight / .bias f32 [128], attention.k_normalization.weight / .bias f32 [128],
+ *     attention.wo.weight bf16 [d][H 128], ffn_norm.weight f32 [d], feed_forward.w13.weight bf16 [2F][d],
+ *     feed_forward.w2.weight bf16 [d][F]
+ *   then norm.weight f32 [d], output.weight bf16 [V][d]
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct wmar_cham_config {
+    int vocab_size, dim, n_layer, n_head, n_kv_head;
+    int ffn_hidden;       /* F: the FeedForward hidden size after the multiple_of rounding (11008 for 7B)          */
+    int max_seq;          /* cache positions per row: longest prompt + generated tokens                            */
+    int max_batch;        /* images per call, <= 5 (3B guided rows <= 16)                                          */
+    int image_token_lo, image_token_hi; /* allowed ids [lo, hi): vocab.image_tokens (4..8195 for Chameleon)        */
+    float norm_eps, rope_theta;
+    int qk_norm;          /* ModelArgs.qk_normalization                                                            */
+} wmar_cham_config;
+
+typedef struct wmar_cham wmar_cham;
+
+int wmar_cham_create(const wmar_cham_config *cfg, const void *const *d_weights, int n_weights, wmar_cham **out);
+void wmar_cham_destroy(wmar_cham *g);
+/* d_prompts int64 [3B][max_prompt] (rows: B full-conditioned, B image-conditioned, B unconditioned prompts, each ending
+ * in <boi>, left-aligned), d_prompt_len int32 [3B], p_max = the longest prompt.  d_noise fp32 [steps][B][V] (the
+ * Exp(1) draws of torch.multinomial over the full vocabulary) or NULL; d_out_ids int64 [B][steps];
+ * d_out_logits (optional) fp32 [steps][B][hi-lo] = the mixed logits of the image-token window before the watermark. */
+int wmar_cham_sample(wmar_cham *g, const wmar_wm_params *wm, const wmar_sample_params *sp, const int64_t *d_prompts,
+                     const int32_t *d_prompt_len, int64_t max_prompt, int64_t p_max, int64_t B, float guidance_text,
+                     float guidance_image, int64_t steps, const float *d_noise, int64_t *d_out_ids, float *d_out_logits,
+                     void *stream);
+double wmar_cham_algorithmic_bytes(const wmar_cham *g, int64_t B, int64_t p_max, int64_t steps);
+int wmar_cham_launches_per_pass(const wmar_cham *g);
+/* The logits-processor + token-selector operator of ImageDecoder on GIVEN logits (chameleon.py:312-346, generation.py:
+ * 86-97): d_logits3 fp32 [3B][V] (full | image-conditioned | unconditioned rows) -> mixed = u + s_img (i-u) + s_txt (f-i)
+ * -> watermark -> allow only ids [lo, hi) -> /T -> top-p -> softmax -> multinomial (d_noise fp32 [B][V] Exp(1), or
+ * NULL = Philox) or argmax.  d_mixed fp32 [B][hi-lo] receives the mixed logits of the window; d_out_ids int64 [B]. */
+int wmar_cham_select(const wmar_wm_params *wm, const wmar_sample_params *sp, const float *d_logits3, int64_t B, int64_t V,
+                     int64_t image_token_lo, int64_t image_token_hi, float guidance_text, float guidance_image,
+                     const int64_t *d_past_ids, int64_t t, int64_t past_stride, const float *d_noise, int64_t *d_out_ids,
+                     float *d_mixed, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * VQGAN tokenizer (Taming / Chameleon family and MaskGIT / RAR family).
  * Replaces codes_to_images / images_to_codes (taming_wrapper.py:79-92, rar_wrapper.py:109-128) and below them

@@ -35,6 +35,13 @@ class RarConfig(ctypes.Structure):
                 ("max_batch", ctypes.c_int)]
 
 
+class ChamConfig(ctypes.Structure):
+    _fields_ = [("vocab_size", ctypes.c_int), ("dim", ctypes.c_int), ("n_layer", ctypes.c_int), ("n_head", ctypes.c_int),
+                ("n_kv_head", ctypes.c_int), ("ffn_hidden", ctypes.c_int), ("max_seq", ctypes.c_int),
+                ("max_batch", ctypes.c_int), ("image_token_lo", ctypes.c_int), ("image_token_hi", ctypes.c_int),
+                ("norm_eps", ctypes.c_float), ("rope_theta", ctypes.c_float), ("qk_norm", ctypes.c_int)]
+
+
 class VqganConfig(ctypes.Structure):
     _fields_ = [("family", ctypes.c_int), ("ch", ctypes.c_int), ("n_levels", ctypes.c_int),
                 ("ch_mult", ctypes.c_int * 8), ("num_res_blocks", ctypes.c_int), ("attn_resolution", ctypes.c_int),
@@ -76,6 +83,19 @@ EXPORTS = {
                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_float, c_voidp, c_voidp, c_voidp,
                                        c_voidp]),
     "wmar_rar_algorithmic_bytes": (ctypes.c_double, [c_voidp, ctypes.c_int64, ctypes.c_int64]),
+    "wmar_skinny_gemm_bf16": (ctypes.c_int, [c_voidp, c_voidp, c_voidp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                             c_voidp]),
+    "wmar_cham_create": (ctypes.c_int, [ctypes.POINTER(ChamConfig), ctypes.POINTER(c_voidp), ctypes.c_int,
+                                        ctypes.POINTER(c_voidp)]),
+    "wmar_cham_destroy": (None, [c_voidp]),
+    "wmar_cham_sample": (ctypes.c_int, [c_voidp, ctypes.POINTER(WmParams), ctypes.POINTER(SampleParams), c_voidp, c_voidp,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
+                                        ctypes.c_int64, c_voidp, c_voidp, c_voidp, c_voidp]),
+    "wmar_cham_algorithmic_bytes": (ctypes.c_double, [c_voidp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]),
+    "wmar_cham_launches_per_pass": (ctypes.c_int, [c_voidp]),
+    "wmar_cham_select": (ctypes.c_int, [ctypes.POINTER(WmParams), ctypes.POINTER(SampleParams), c_voidp, ctypes.c_int64,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
+                                        c_voidp, ctypes.c_int64, ctypes.c_int64, c_voidp, c_voidp, c_voidp, c_voidp]),
     "wmar_vqgan_create": (ctypes.c_int, [ctypes.POINTER(VqganConfig), ctypes.POINTER(c_voidp), ctypes.c_int,
                                          ctypes.POINTER(c_voidp)]),
     "wmar_vqgan_destroy": (None, [c_voidp]),

@@ -147,16 +147,28 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const float *_
     const float4 q4 = *reinterpret_cast<const float4 *>(q + 4 * sub);
     const float scale = 1.0f / sqrtf((float)HD);
     const int nk = t + 1;
-    for (int j0 = 0; j0 < nk; j0 += GROUPS) {
-        const int j = j0 + grp;
-        float s = 0.f;
-        if (j < nk) {
-            float4 k4 = *reinterpret_cast<const float4 *>(K + (size_t)j * HD + 4 * sub);
-            s = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-        }
+    // the phase is memory-latency bound: 8 keys per group in flight at a time
+    constexpr int BATCH = 8;
+    for (int jb = 0; jb < nk; jb += GROUPS * BATCH) {   // warp-uniform trip count: the shuffles below use the full mask
+        const int j0 = jb + grp;
+        float4 k4[BATCH];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (j < nk && sub == 0) sc[j] = s * scale;
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + u * GROUPS;
+            k4[u] = j < nk ? *reinterpret_cast<const float4 *>(K + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float sd[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) sd[u] = q4.x * k4[u].x + q4.y * k4[u].y + q4.z * k4[u].z + q4.w * k4[u].w;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], o);
+        if (sub == 0) {
+#pragma unroll
+            for (int u = 0; u < BATCH; u++)
+                if (j0 + u * GROUPS < nk) sc[j0 + u * GROUPS] = sd[u] * scale;
+        }
     }
     __syncthreads();
     float m = -INFINITY;
@@ -182,10 +194,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const float *_
     for (int w = 0; w < ATT_THREADS / 32; w++) sum += red[w];
     const float inv = 1.0f / sum;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = grp; j < nk; j += GROUPS) {
-        const float p = sc[j] * inv;
-        float4 v4 = *reinterpret_cast<const float4 *>(Vc + (size_t)j * HD + 4 * sub);
-        acc.x += p * v4.x; acc.y += p * v4.y; acc.z += p * v4.z; acc.w += p * v4.w;
+    for (int jb = 0; jb < nk; jb += GROUPS * BATCH) {
+        const int j0 = jb + grp;
+        float4 v4[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + u * GROUPS;
+            v4[u] = j < nk ? *reinterpret_cast<const float4 *>(Vc + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + u * GROUPS;
+            const float p = j < nk ? sc[j] * inv : 0.f;
+            acc.x += p * v4[u].x; acc.y += p * v4[u].y; acc.z += p * v4[u].z; acc.w += p * v4[u].w;
+        }
     }
     *reinterpret_cast<float4 *>(&part[grp][4 * sub]) = acc;
     __syncthreads();

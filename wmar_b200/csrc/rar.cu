@@ -170,14 +170,29 @@ __global__ void __launch_bounds__(RAR_ATT_THREADS) rar_attn_kernel(const float *
     const float scale = 1.0f / sqrtf((float)hd);
     const int nk = i + 1;
     const int hd4 = hd >> 2;
-    for (int j = warp; j < nk; j += 8) {
-        float s = 0.f;
-        if (lane < hd4) {
-            float4 k4 = *reinterpret_cast<const float4 *>(K + (size_t)j * hd + 4 * lane);
-            s = sq[4 * lane] * k4.x + sq[4 * lane + 1] * k4.y + sq[4 * lane + 2] * k4.z + sq[4 * lane + 3] * k4.w;
+    // memory-latency bound: 8 keys per warp in flight at a time
+    constexpr int BATCH = 8;
+    const int lc = lane < hd4 ? lane : 0;
+    const float4 q4 = *reinterpret_cast<const float4 *>(sq + 4 * lc);
+    for (int j0 = warp; j0 < nk; j0 += 8 * BATCH) {
+        float4 k4[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + 8 * u;
+            k4[u] = (j < nk && lane < hd4) ? *reinterpret_cast<const float4 *>(K + (size_t)j * hd + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        s = warp_sum(s);
-        if (lane == 0) sc[j] = s * scale;
+        float sd[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) sd[u] = q4.x * k4[u].x + q4.y * k4[u].y + q4.z * k4[u].z + q4.w * k4[u].w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < BATCH; u++)
+                if (j0 + 8 * u < nk) sc[j0 + 8 * u] = sd[u] * scale;
+        }
     }
     __syncthreads();
     float m = -INFINITY;
@@ -203,11 +218,18 @@ __global__ void __launch_bounds__(RAR_ATT_THREADS) rar_attn_kernel(const float *
     for (int w = 0; w < 8; w++) sum += red[w];
     const float inv = 1.0f / sum;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = warp; j < nk; j += 8) {
-        if (lane < hd4) {
-            const float p = sc[j] * inv;
-            float4 v4 = *reinterpret_cast<const float4 *>(V + (size_t)j * hd + 4 * lane);
-            acc.x += p * v4.x; acc.y += p * v4.y; acc.z += p * v4.z; acc.w += p * v4.w;
+    for (int j0 = warp; j0 < nk; j0 += 8 * BATCH) {
+        float4 v4[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + 8 * u;
+            v4[u] = (j < nk && lane < hd4) ? *reinterpret_cast<const float4 *>(V + (size_t)j * hd + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + 8 * u;
+            const float p = j < nk ? sc[j] * inv : 0.f;
+            acc.x += p * v4[u].x; acc.y += p * v4[u].y; acc.z += p * v4[u].z; acc.w += p * v4[u].w;
         }
     }
     if (lane < hd4) *reinterpret_cast<float4 *>(&part[warp][4 * lane]) = acc;

@@ -25,6 +25,10 @@ struct SampleArgs {
     int greedy;
     unsigned long long seed;
     int cand_cap;  // capacity of the candidate arrays (power of two), 0 when top-p is off
+    // id window (Chameleon: only the image tokens [id_base, id_base + V) are allowed, logits_processor.py:135-151):
+    // logits_row / noise_row point at the window, the greenlist table still covers the full vocabulary table_V
+    int id_base;   // 0 = no window
+    int table_V;   // 0 = V
 };
 
 __host__ __device__ inline size_t sample_smem_bytes(int V, int cand_cap) {
@@ -137,13 +141,14 @@ __device__ inline int sample_row(const SampleArgs &a, const float *__restrict__ 
     if (a.table != nullptr) {
         long long s = context_sum(past, t, a.seed_strategy, a.h, a.spatial_dim);
         if (s >= 0) {
-            if (s < a.n_rows) row = a.table + s * (long long)((V + 31) / 32);
+            if (s < a.n_rows) row = a.table + s * (long long)(((a.table_V > 0 ? a.table_V : V) + 31) / 32);
             else if (tid == 0) atomicOr(err, 1);
         }
     }
     for (int v = tid; v < V; v += SAMPLE_THREADS) {
         float l = logits_row[v];
-        if (row != nullptr && ((row[v >> 5] >> (v & 31)) & 1u)) l += a.delta;
+        const int gv = v + a.id_base;
+        if (row != nullptr && ((row[gv >> 5] >> (gv & 31)) & 1u)) l += a.delta;
         vals[v] = l / a.temperature;
     }
     __syncthreads();
@@ -264,7 +269,7 @@ __device__ inline int sample_row(const SampleArgs &a, const float *__restrict__ 
         }
         if (sc > best) { best = sc; best_i = v; }  // ascending v within a thread keeps the first index on ties
     }
-    return block_argmax(best, best_i, red_v, red_i);
+    return block_argmax(best, best_i, red_v, red_i) + a.id_base;
 }
 
 }  // namespace wmar
