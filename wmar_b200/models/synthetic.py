@@ -208,3 +208,35 @@ def rar_state(cfg=RAR_XL_CFG, seed=0, device="cpu", prefix=""):
     w["lm_head.weight"] = G.rn(codebook, d, std=0.02)
     w["lm_head.bias"] = G.rn(codebook, std=0.01)
     return {prefix + k: v for k, v in w.items()}
+
+
+# Anole-7B / Chameleon-7B (deps/chameleon/inference/transformer.py ModelArgs as loaded from params.json of the 7B
+# checkpoint: dim 4096, 32 layers, 32 heads, ffn hidden 11008, vocab 65536, qk_normalization, no swin norm) and its
+# 512-pixel VQGAN (deps/chameleon/inference/vqgan.py ddconfig: 6 levels, attention only in `mid`, 8192 codes)
+ANOLE_7B_CFG = dict(vocab_size=65536, dim=4096, n_layers=32, n_heads=32, n_kv_heads=32, ffn_hidden=11008,
+                    norm_eps=1e-5, rope_theta=10000.0, qk_normalization=True)
+CHAMELEON_VQGAN_DDCONFIG = dict(ch=128, out_ch=3, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, attn_resolutions=(),
+                                in_channels=3, resolution=512, z_channels=256, n_embed=8192, embed_dim=256)
+
+
+def chameleon_state(cfg=ANOLE_7B_CFG, seed=0, device="cpu"):
+    """bf16 state dict with the reference Transformer's parameter names; created layer by layer on `device`."""
+    G = _Gen(seed, device)
+    bf = torch.bfloat16
+    V, d, L, H, Hkv, F = cfg["vocab_size"], cfg["dim"], cfg["n_layers"], cfg["n_heads"], cfg["n_kv_heads"], cfg["ffn_hidden"]
+    hd = d // H
+    w = {"tok_embeddings.weight": G.rn(V, d, std=1.0).to(bf), "norm.weight": G.rn(d, std=0.1, mean=1.0).to(bf),
+         "output.weight": G.rn(V, d, std=0.02).to(bf)}
+    for i in range(L):
+        p = f"layers.{i}."
+        w[p + "attention_norm.weight"] = G.rn(d, std=0.1, mean=1.0).to(bf)
+        w[p + "ffn_norm.weight"] = G.rn(d, std=0.1, mean=1.0).to(bf)
+        w[p + "attention.wqkv.weight"] = G.rn((H + 2 * Hkv) * hd, d, std=0.02).to(bf)
+        w[p + "attention.wo.weight"] = G.rn(d, H * hd, std=0.02).to(bf)
+        if cfg.get("qk_normalization", True):
+            for nm in ("q_normalization", "k_normalization"):
+                w[p + f"attention.{nm}.weight"] = G.rn(hd, std=0.1, mean=1.0).to(bf)
+                w[p + f"attention.{nm}.bias"] = G.rn(hd, std=0.05).to(bf)
+        w[p + "feed_forward.w13.weight"] = G.rn(2 * F, d, std=0.02).to(bf)
+        w[p + "feed_forward.w2.weight"] = G.rn(d, F, std=0.02).to(bf)
+    return w
