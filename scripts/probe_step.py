@@ -50,7 +50,8 @@ def main():
         import ctypes
         from wmar_b200 import _lib
         _lib.lib().wmar_debug_set_gemm_engine.argtypes = [ctypes.c_int]
-        _lib.lib().wmar_debug_set_gemm_engine(1 if mode == "graph_v0" else 0)
+        if mode in ("graph_v0", "graph_tc"):   # "graph" / "fused" keep the library default (mma.sync engine)
+            _lib.lib().wmar_debug_set_gemm_engine(1 if mode == "graph_v0" else 0)
         eng = TamingGPTEngine(w, L, H)
         for rep in range(reps):
             torch.cuda.synchronize()
