@@ -89,7 +89,7 @@ __device__ __forceinline__ void combine_row_stats(const float2 *__restrict__ sta
     float n = 0.f, mean = 0.f, m2 = 0.f;
     const float w = (float)(K / n_tiles);
     for (int tl = sub; tl < n_tiles; tl += 16) {
-        float2 s = stats_in[tl * 16 + r];
+        float2 s = __ldcg(stats_in + tl * 16 + r);   // not hoistable above griddepcontrol.wait
         chan_combine(n, mean, m2, w, s.x, s.y);
     }
 #pragma unroll

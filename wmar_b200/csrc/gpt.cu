@@ -124,38 +124,50 @@ __global__ void __launch_bounds__(256) embed_kernel(const CallParams *cp, const 
 
 // One CTA per (head, row).  Appends this step's k,v to the cache and attends over keys 0..t.
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const float *__restrict__ qkv, int d, int H, int T,
-                                                                  float *__restrict__ kcache, float *__restrict__ vcache,
+__global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const float *qkv, int d, int H, int T,
+                                                                  float *kcache, float *vcache,
                                                                   int layer, const int *step, float *__restrict__ y) {
+    // NOTE: qkv / the caches are NOT __restrict__: the compiler may hoist loads through read-only (__restrict__ const)
+    // pointers above griddepcontrol.wait, i.e. read q,k,v before the producing GEMM has written them.
     static_assert(HD == 64, "Taming head_dim");
     __shared__ float sc[1024];                      // scores / probabilities (T <= 1024)
     __shared__ __align__(16) float part[ATT_THREADS / 16][HD];
     __shared__ float red[ATT_THREADS / 32];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // qkv comes from the previous kernel
-    const int h = blockIdx.x, b = blockIdx.y, t = *step;
+    const int h = blockIdx.x, b = blockIdx.y, t = *step;   // the step counter was advanced before the previous kernel
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = tid & 15, grp = tid >> 4;       // 16 lanes per key, ATT_THREADS/16 keys in flight
     constexpr int GROUPS = ATT_THREADS / 16;
+    constexpr int BATCH = 8;                        // keys per group in flight at a time (the phase is latency bound)
     const float *q = qkv + (size_t)b * 3 * d + h * HD;
     const float *kn = q + d, *vn = q + 2 * d;
     const size_t base = (((size_t)layer * 16 + b) * H + h) * (size_t)T * HD;
     float *K = kcache + base, *Vc = vcache + base;
-    if (tid < 16) *reinterpret_cast<float4 *>(K + (size_t)t * HD + 4 * tid) = *reinterpret_cast<const float4 *>(kn + 4 * tid);
-    else if (tid < 32) *reinterpret_cast<float4 *>(Vc + (size_t)t * HD + 4 * (tid - 16)) = *reinterpret_cast<const float4 *>(vn + 4 * (tid - 16));
-    __syncthreads();
-    const float4 q4 = *reinterpret_cast<const float4 *>(q + 4 * sub);
-    const float scale = 1.0f / sqrtf((float)HD);
     const int nk = t + 1;
-    // the phase is memory-latency bound: 8 keys per group in flight at a time
-    constexpr int BATCH = 8;
+    // K and V rows of EARLIER steps are final: the first 128 keys of both are fetched before waiting for this step's
+    // q,k,v (two of the four memory round trips of the kernel overlap the tail of the qkv GEMM)
+    float4 k4a[BATCH], v4a[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) {
+        const int j = grp + u * GROUPS;
+        k4a[u] = j < t ? *reinterpret_cast<const float4 *>(K + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v4a[u] = j < t ? *reinterpret_cast<const float4 *>(Vc + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // qkv comes from the previous kernel
+    const float4 q4 = __ldcg(reinterpret_cast<const float4 *>(q + 4 * sub));
+    const float4 kn4 = __ldcg(reinterpret_cast<const float4 *>(kn + 4 * sub)), vn4 = __ldcg(reinterpret_cast<const float4 *>(vn + 4 * sub));
+    if (tid < 16) *reinterpret_cast<float4 *>(K + (size_t)t * HD + 4 * tid) = kn4;             // append for later steps
+    else if (tid < 32) *reinterpret_cast<float4 *>(Vc + (size_t)t * HD + 4 * (tid - 16)) = vn4;
+    const float scale = 1.0f / sqrtf((float)HD);
     for (int jb = 0; jb < nk; jb += GROUPS * BATCH) {   // warp-uniform trip count: the shuffles below use the full mask
         const int j0 = jb + grp;
         float4 k4[BATCH];
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             const int j = j0 + u * GROUPS;
-            k4[u] = j < nk ? *reinterpret_cast<const float4 *>(K + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j == t) k4[u] = kn4;                                    // this step's own key (not read back from the cache)
+            else if (jb == 0) k4[u] = k4a[u];
+            else k4[u] = j < t ? *reinterpret_cast<const float4 *>(K + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float sd[BATCH];
 #pragma unroll
@@ -200,7 +212,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const float *_
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             const int j = j0 + u * GROUPS;
-            v4[u] = j < nk ? *reinterpret_cast<const float4 *>(Vc + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j == t) v4[u] = vn4;
+            else if (jb == 0) v4[u] = v4a[u];
+            else v4[u] = j < t ? *reinterpret_cast<const float4 *>(Vc + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
