@@ -198,8 +198,9 @@ int wmar_skinny_gemm_bf16(const float *d_x, const void *d_w_bf16, float *d_y, in
  *   [0] tok_embeddings.weight bf16 [V][d]
  *   per layer l (10 entries, base 1 + 10 l): attention_norm.weight f32 [d], attention.wqkv.weight bf16 [(H+2Hkv)128][d],
  *     attention.q_normalization.weight / .bias f32 [128], attention.k_normalization.weight / .bias f32 [128],
- *     attention.wo.weight bf16 [d][H 128], ffn_norm.weight f32 [d], feed_forward.w13.weight bf16 [2F][d],
- *     feed_forward.w2.weight bf16 [d][F]
+ *     attention.wo.weight bf16 [d][H 128], ffn_norm.weight f32 [d], feed_forward.w13.weight bf16 [2F][d] with its rows
+ *     INTERLEAVED per 64-row tile (rows 64T..64T+31 = w1 rows 32T..32T+31, rows 64T+32..64T+63 = w3 rows 32T..32T+31, so
+ *     that the GEMM epilogue can form silu(x1) * x3), feed_forward.w2.weight bf16 [d][F]
  *   then norm.weight f32 [d], output.weight bf16 [V][d]
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct wmar_cham_config {

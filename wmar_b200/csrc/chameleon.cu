@@ -15,7 +15,8 @@
 //     q,k  = RoPE(q,k; interleaved pairs, theta, position p) ; append k,v to the bf16 cache     :130-138 (xformers)
 //     y    = softmax(q K^T / sqrt(hd)) V  over keys 0..p of the row      :149-156
 //     x    = bf16( x + bf16(y Wo^T) )                                    :158,238-244
-//     h13  = bf16( RMSNorm(x) W13^T ) ; x = bf16( x + bf16( (silu(x1) * x3) W2^T ) )           :215-219,245
+//     h    = bf16( bf16(silu(x1)) * x3 ),  [x1|x3] = bf16( RMSNorm(x) W13^T )  (fused into the w13 epilogue)   :215-218
+//     x    = bf16( x + bf16( h W2^T ) )                                    :219,245
 //   logits = bf16( RMSNorm(x) Wout^T ).float()                           :314-319
 // Sampling (passes >= Pmax - 1), chameleon.py:312-327 + generation.py:86-97:
 //     mixed = u + s_img (i - u) + s_txt (f - i)  ->  +delta on green  ->  -inf outside the image tokens  ->  / T
@@ -398,14 +399,16 @@ int cham_enqueue_pass(wmar_cham *g, int B, size_t sample_smem, cudaStream_t s) {
         if ((rc = launch_skinny_gemm_bf16(BPRO_NONE, BEPI_RESID, o, s))) return rc;
         Bf16GemmArgs f{};
         f.ws = g->ws; f.counters = g->counters; f.eps = c.norm_eps;
-        f.X = g->x; f.ldx = d; f.W = L.w13; f.Y = g->h13; f.ldy = 2 * F; f.N = 2 * F; f.K = d; f.splits = g->s_w13;
+        // w13 rows are interleaved by the host packer (32 x1 rows, then their 32 x3 rows, per 64-row tile): the epilogue
+        // writes h = silu(x1) * x3 directly
+        f.X = g->x; f.ldx = d; f.W = L.w13; f.Y = g->h13; f.ldy = F; f.N = 2 * F; f.K = d; f.splits = g->s_w13;
         f.rms_w = L.ffn_norm; f.stats_in = g->stats; f.n_stat_tiles = stat_tiles;
-        if ((rc = launch_skinny_gemm_bf16(BPRO_RMS, BEPI_STORE, f, s))) return rc;
+        if ((rc = launch_skinny_gemm_bf16(BPRO_RMS, BEPI_SWIGLU, f, s))) return rc;
         Bf16GemmArgs w{};
         w.ws = g->ws; w.counters = g->counters;
-        w.X = g->h13; w.ldx = 2 * F; w.W = L.w2; w.Y = g->x; w.ldy = d; w.N = d; w.K = F; w.splits = g->s_w2;
-        w.swiglu_off = F; w.resid = g->x; w.ld_resid = d; w.stats_out = g->stats;
-        if ((rc = launch_skinny_gemm_bf16(BPRO_SWIGLU, BEPI_RESID, w, s))) return rc;
+        w.X = g->h13; w.ldx = F; w.W = L.w2; w.Y = g->x; w.ldy = d; w.N = d; w.K = F; w.splits = g->s_w2;
+        w.resid = g->x; w.ld_resid = d; w.stats_out = g->stats;
+        if ((rc = launch_skinny_gemm_bf16(BPRO_NONE, BEPI_RESID, w, s))) return rc;
         launches += 5;
     }
     Bf16GemmArgs hd{};
@@ -436,6 +439,7 @@ int wmar_cham_create(const wmar_cham_config *cfg, const void *const *d_weights, 
     WMAR_REQUIRE(cfg->n_head > 0 && cfg->n_kv_head > 0 && cfg->n_head % cfg->n_kv_head == 0, "n_head must be a multiple of n_kv_head");
     WMAR_REQUIRE(cfg->dim % cfg->n_head == 0 && cfg->dim / cfg->n_head == CH_HD, "this engine supports head_dim 128 (Chameleon)");
     WMAR_REQUIRE(cfg->dim % 64 == 0 && cfg->vocab_size % 64 == 0 && cfg->ffn_hidden % 64 == 0, "dim, vocab and ffn_hidden must be multiples of 64");
+    WMAR_REQUIRE(cfg->ffn_hidden % 32 == 0, "ffn_hidden must be a multiple of 32 (w13 row interleave)");
     WMAR_REQUIRE(cfg->max_seq >= 2 && cfg->max_seq <= 4096, "max_seq must be in [2,4096]");
     WMAR_REQUIRE(cfg->max_batch >= 1 && 3 * cfg->max_batch <= 16, "max_batch must be in [1,5] (3B guided rows <= 16)");
     WMAR_REQUIRE(cfg->image_token_lo >= 0 && cfg->image_token_hi > cfg->image_token_lo && cfg->image_token_hi <= cfg->vocab_size,

@@ -23,9 +23,15 @@ static bool v0_pdl() {
 
 template <int PRO, int EPI>
 static int launch_t(const GemmArgs &a, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        configured = true;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(a.N / GEMM_NT), (unsigned)a.splits, 1);
     cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -124,8 +130,10 @@ extern "C" int wmar_skinny_gemm(const float *d_x, const float *d_w, const float 
     a.ws = g_ws; a.counters = g_counters;
     if (g_probe_mode != 0) {
         dim3 grid((unsigned)(a.N / GEMM_NT), (unsigned)a.splits);
-        if (g_probe_mode == 1) skinny_gemm_kernel<PRO_NONE, EPI_STORE, 1><<<grid, GEMM_THREADS, 0, as_stream(stream)>>>(a);
-        else skinny_gemm_kernel<PRO_NONE, EPI_STORE, 2><<<grid, GEMM_THREADS, 0, as_stream(stream)>>>(a);
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO_NONE, EPI_STORE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO_NONE, EPI_STORE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        if (g_probe_mode == 1) skinny_gemm_kernel<PRO_NONE, EPI_STORE, 1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, as_stream(stream)>>>(a);
+        else skinny_gemm_kernel<PRO_NONE, EPI_STORE, 2><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, as_stream(stream)>>>(a);
         WMAR_LAUNCH_CHECK();
         return WMAR_OK;
     }

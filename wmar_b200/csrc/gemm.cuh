@@ -3,8 +3,12 @@
 // Replaces every nn.Linear of the per-token step (mingpt.py:53-60,105-110,142; rar.py:75,79,127-129,173-176,232).
 // The step is HBM-bound on W (each weight is used for only 16 rows), so the kernel is built around streaming W once
 // with as many 16-byte loads in flight as possible and doing the math on the tensor pipe:
-//   * the 16 batch rows are exactly the M of mma.m16n8k8; W rows map to the MMA's n, so W goes HBM -> registers as
-//     B fragments with NO shared-memory staging (one LDG.128 per lane covers two k8 steps of one n8 tile),
+//   * the 16 batch rows are exactly the M of mma.m16n8k8; W rows map to the MMA's n, and every lane fetches exactly
+//     the 16-byte pieces that are ITS B fragments (one piece covers two k8 steps of one n8 tile).  The pieces travel
+//     with cp.async through a per-warp, per-lane private shared-memory ring (3 stages x 4 KB per warp): shared memory
+//     is used purely as extra load-queue depth -- up to three iterations of every warp are in flight at once (96 KB
+//     per CTA, 192 KB per SM) instead of the two a register double buffer allows, and a lane only ever reads back what
+//     it wrote itself, so there is no barrier and no bank conflict,
 //   * products are 3xTF32 (hi*hi + hi*lo + lo*hi with fp32 accumulation): fp32-faithful results, which the
 //     reference's fp32 (TF32-off) Linear layers require for greedy token parity,
 //   * split-K across CTAs (grid.y) fills all 148 SMs even for N = 1536; partial tiles go to an L2-resident workspace
@@ -23,6 +27,11 @@ constexpr int GEMM_TILES = GEMM_NT / 8;
 constexpr int GEMM_KI = 16;      // k per warp iteration (one LDG.128 per lane per n8 tile)
 constexpr int GEMM_M = 16;       // batch rows
 constexpr int GEMM_RED_LD = 72;  // padded row of the cross-warp reduction buffer
+constexpr int GEMM_STAGES = 3;   // cp.async ring depth per warp
+constexpr int GEMM_STAGE_BYTES = GEMM_TILES * 32 * 16;                         // 4 KB: [n8 tile][lane][16 B]
+constexpr int GEMM_RING_BYTES = GEMM_WARPS * GEMM_STAGES * GEMM_STAGE_BYTES;   // 96 KB per CTA
+constexpr int GEMM_RED_BYTES = GEMM_WARPS * GEMM_M * GEMM_RED_LD * 4;          // aliases the ring after the main loop
+constexpr int GEMM_SMEM_BYTES = GEMM_RING_BYTES > GEMM_RED_BYTES ? GEMM_RING_BYTES : GEMM_RED_BYTES;
 
 enum GemmPrologue { PRO_NONE = 0, PRO_LN = 1, PRO_ADALN = 2 };
 enum GemmEpilogue { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_GATE_RESID = 3 };
@@ -53,6 +62,14 @@ __device__ __forceinline__ float4 ldg_stream(const float *p) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+// 16-byte asynchronous copy global -> shared, L2 only (the weights are streamed once)
+__device__ __forceinline__ void gm_cp16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gm_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void gm_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ uint32_t tf32_hi(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -106,7 +123,8 @@ __device__ __forceinline__ void combine_row_stats(const float2 *__restrict__ sta
 
 template <int PRO, int EPI, int MODE = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a) {
-    __shared__ __align__(16) float red[GEMM_WARPS * GEMM_M * GEMM_RED_LD];
+    extern __shared__ __align__(16) uint8_t gemm_smem[];
+    float *red = reinterpret_cast<float *>(gemm_smem);   // cross-warp reduction buffer: aliases the drained ring
     __shared__ float2 row_stats[GEMM_M];
     __shared__ int s_is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -121,11 +139,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
     const int iters = warp < chunks ? (chunks - warp + GEMM_WARPS - 1) / GEMM_WARPS : 0;
     constexpr int KSTEP = GEMM_WARPS * GEMM_KI;
 
-    // issue the first weight loads before anything else: they do not depend on the producer kernel
+    // issue the weight loads of the first GEMM_STAGES iterations before anything else: they do not depend on the
+    // producer kernel.  One commit group per iteration (empty groups keep the count constant).
     const float *wbase = a.W + (size_t)(n0 + g) * a.K + kw0 + 4 * t;
-    float4 wcur[GEMM_TILES];
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(gemm_smem) + (uint32_t)(warp * GEMM_STAGES * GEMM_STAGE_BYTES) + (uint32_t)(lane * 16);
+    auto issue = [&](int it) {
+        if (it < iters) {
+            const uint32_t dst = ring + (uint32_t)((it % GEMM_STAGES) * GEMM_STAGE_BYTES);
 #pragma unroll
-    for (int j = 0; j < GEMM_TILES; j++) wcur[j] = iters > 0 ? ldg_stream(wbase + (size_t)(8 * j) * a.K) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < GEMM_TILES; j++) gm_cp16(dst + j * 512, wbase + (size_t)(8 * j) * a.K + it * KSTEP);
+        }
+        gm_cp_commit();
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < GEMM_STAGES; s0++) issue(s0);
     // programmatic dependent launch: the next kernel of the step may start (and issue ITS first weight loads) while this
     // one runs; everything below reads what the previous kernel produced
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -149,12 +176,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
     const float *x_g8 = a.X + (size_t)(g + 8) * a.ldx + kw0 + 4 * t;
 
     for (int it = 0; it < iters; it++) {
-        // prefetch next iteration's weights
-        float4 wnext[GEMM_TILES];
-        if (it + 1 < iters) {
-#pragma unroll
-            for (int j = 0; j < GEMM_TILES; j++) wnext[j] = ldg_stream(wbase + (size_t)(8 * j) * a.K + (it + 1) * KSTEP);
-        }
         const int koff = it * KSTEP;
         float4 xa = *reinterpret_cast<const float4 *>(x_g + koff);
         float4 xb = *reinterpret_cast<const float4 *>(x_g8 + koff);
@@ -192,6 +213,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
         for (int r = 0; r < 2; r++)
 #pragma unroll
             for (int e = 0; e < 4; e++) split_tf32(xs[r][e], xh[r][e], xl[r][e]);
+        // this iteration's weights have landed (at most STAGES-1 newer groups may still be in flight); pull them into
+        // registers and hand the stage to iteration it + STAGES
+        gm_cp_wait<GEMM_STAGES - 1>();
+        float4 wcur[GEMM_TILES];
+        {
+            const uint8_t *src = gemm_smem + (warp * GEMM_STAGES + (it % GEMM_STAGES)) * GEMM_STAGE_BYTES + lane * 16;
+#pragma unroll
+            for (int j = 0; j < GEMM_TILES; j++) wcur[j] = *reinterpret_cast<const float4 *>(src + j * 512);
+        }
+        issue(it + GEMM_STAGES);
 #pragma unroll
         for (int j = 0; j < GEMM_TILES; j++) {
             const float wv[4] = {wcur[j].x, wcur[j].y, wcur[j].z, wcur[j].w};
@@ -210,11 +241,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
                 else acc[j][e] += __uint_as_float(wh[e]) + __uint_as_float(wh[e + 1]);
             }
         }
-        if (it + 1 < iters) {
-#pragma unroll
-            for (int j = 0; j < GEMM_TILES; j++) wcur[j] = wnext[j];
-        }
     }
+    gm_cp_wait<0>();
+    __syncthreads();   // every warp is done with its ring: the reduction buffer below aliases it
 
     // ---- cross-warp reduction (fixed order) ----
     float *myred = red + warp * GEMM_M * GEMM_RED_LD;

@@ -5,9 +5,22 @@ namespace wmar {
 
 template <int PRO, int EPI>
 static int launch_bf16_t(const Bf16GemmArgs &a, cudaStream_t stream) {
+    static int n_sms = 0;
+    if (!n_sms) {
+        int dev = 0;
+        WMAR_CUDA_CHECK(cudaGetDevice(&dev));
+        WMAR_CUDA_CHECK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int items = (a.N / GEMM_NT) * a.splits;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(a.N / GEMM_NT), (unsigned)a.splits, 1);
+    cfg.gridDim = dim3((unsigned)(items < 2 * n_sms ? items : 2 * n_sms), 1, 1);   // persistent: two CTAs per SM
+    static bool configured = false;
+    if (!configured) {
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_bf16_kernel<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        configured = true;
+    }
     cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -31,19 +44,26 @@ int launch_skinny_gemm_bf16(int pro, int epi, const Bf16GemmArgs &a, cudaStream_
     WMAR_CASE(BPRO_RMS, BEPI_STORE)
     WMAR_CASE(BPRO_RMS, BEPI_STORE_F32)
     WMAR_CASE(BPRO_SWIGLU, BEPI_RESID)
+    WMAR_CASE(BPRO_RMS, BEPI_SWIGLU)
     WMAR_CASE(BPRO_NONE, BEPI_STORE_F32)
 #undef WMAR_CASE
     return set_error(WMAR_ERR_INVALID, "unsupported bf16 GEMM prologue/epilogue combination%s%s");
 }
 
 int pick_splits_bf16(int N, int K, int n_sms) {
-    const int tiles = N / GEMM_NT;
-    const int target = 2 * n_sms - 16;
+    // the persistent grid has 2 * n_sms CTAs: pick the smallest split count that fills its waves to >= 85 % while every
+    // item keeps >= 16 chunks of 32 k (two pipelined load rounds per warp)
+    const int tiles = N / GEMM_NT, G = 2 * n_sms;
     int best = 1;
+    double best_eff = 0.0;
     for (int s = 1; s <= 64; s++) {
-        if (K % (s * BG_KI) != 0 || K / (s * BG_KI) < GEMM_WARPS) continue;
-        best = s;
-        if (tiles * s >= target) break;
+        if (K % (s * BG_KI) != 0) continue;
+        if (K / (s * BG_KI) < 16 && s > 1) break;
+        const int items = tiles * s;
+        const int waves = (items + G - 1) / G;
+        const double eff = (double)items / ((double)waves * G);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+        if (eff >= 0.85) break;
     }
     return best;
 }

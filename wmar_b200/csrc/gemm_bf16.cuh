@@ -9,10 +9,18 @@
 //   * the 16 rows (f | i | u guided row groups of <= 5 images) are the M of mma.m16n8k16; W rows are the MMA's n, and W
 //     goes HBM -> registers as B fragments with no shared-memory staging: one LDG.128 per lane = 8 consecutive k of
 //     one weight row = the B fragments of two k16 MMAs (k permuted identically in the A fragments),
-//   * split-K across CTAs with the deterministic last-arriver reduction of gemm.cuh,
+//   * a PERSISTENT grid (two CTAs per SM) walks the (tile, split) work items: the 7B shapes give 256..2048 items, so a
+//     one-item-per-CTA launch would run 1.2-3.5 waves with a ragged tail; the weights travel through the per-lane
+//     cp.async ring of gemm.cuh (three iterations of every warp in flight) and the first three iterations of a CTA's
+//     NEXT item are issued before the split-K tail / epilogue of the current one, so the HBM stream does not drain
+//     inside a kernel,
+//   * split-K with the deterministic last-arriver reduction of gemm.cuh,
 //   * prologues: RMSNorm (xformers RMSNorm, transformer.py:238-239,278) from the producer's (mean, M2) partials;
 //     SwiGLU  silu(x1) * x3  over the two halves of the w13 output (transformer.py:217-218),
-//   * epilogues: round to bf16; residual add (round, add, round) + LayerNorm-style (mean, M2) partials for the next RMS.
+//   * epilogues: round to bf16; residual add (round, add, round) + LayerNorm-style (mean, M2) partials for the next RMS;
+//     SwiGLU: with the rows of w13 interleaved at pack time (tile T = x1 rows 32T..32T+31 then the matching x3 rows) the
+//     epilogue forms h = bf16(bf16(silu(x1)) * x3) once per element and writes [16][F] -- the w2 GEMM then reads half
+//     the activation bytes and evaluates no exp (as a w2 PROLOGUE the same work was redone by each of its 64 tiles).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -23,7 +31,7 @@ namespace wmar {
 constexpr int BG_KI = 32;   // k per warp iteration (one LDG.128 of bf16 per lane per n8 tile)
 
 enum Bf16Prologue { BPRO_NONE = 0, BPRO_RMS = 1, BPRO_SWIGLU = 2 };
-enum Bf16Epilogue { BEPI_STORE = 0, BEPI_RESID = 1, BEPI_STORE_F32 = 2 };
+enum Bf16Epilogue { BEPI_STORE = 0, BEPI_RESID = 1, BEPI_STORE_F32 = 2, BEPI_SWIGLU = 3 };
 
 struct Bf16GemmArgs {
     const float *X; int ldx;
@@ -81,24 +89,33 @@ __device__ __forceinline__ void combine_row_rms(const float2 *__restrict__ stats
 
 template <int PRO, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16GemmArgs a) {
-    __shared__ __align__(16) float red[GEMM_WARPS * GEMM_M * GEMM_RED_LD];
+    extern __shared__ __align__(16) uint8_t gemm_smem[];
+    float *red = reinterpret_cast<float *>(gemm_smem);   // cross-warp reduction buffer: aliases the drained ring
     __shared__ float row_rs[GEMM_M];
     __shared__ int s_is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int tile = blockIdx.x, split = blockIdx.y;
-    const int n0 = tile * GEMM_NT;
+    const int tiles = a.N / GEMM_NT, n_items = tiles * a.splits;
     const int KS = a.K / a.splits;
     const int chunks = KS / BG_KI;
-    const int kw0 = split * KS + warp * BG_KI;
     const int iters = warp < chunks ? (chunks - warp + GEMM_WARPS - 1) / GEMM_WARPS : 0;
     constexpr int KSTEP = GEMM_WARPS * BG_KI;
 
-    // first weight loads: independent of the producer kernel
-    const __nv_bfloat16 *wbase = a.W + (size_t)(n0 + g) * a.K + kw0 + 8 * t;
-    uint4 wcur[GEMM_TILES];
+    // weight loads of iteration `it` of `item` into ring stage it % STAGES: one commit group per call (empty groups keep
+    // the group count constant).  The first STAGES iterations of the first item do not depend on the producer kernel.
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(gemm_smem) + (uint32_t)(warp * GEMM_STAGES * GEMM_STAGE_BYTES) + (uint32_t)(lane * 16);
+    auto issue = [&](int item, int it) {
+        if (item < n_items && it < iters) {
+            const int tl = item % tiles, sp = item / tiles;
+            const __nv_bfloat16 *wb = a.W + (size_t)(tl * GEMM_NT + g) * a.K + sp * KS + warp * BG_KI + 8 * t + it * KSTEP;
+            const uint32_t dst = ring + (uint32_t)((it % GEMM_STAGES) * GEMM_STAGE_BYTES);
 #pragma unroll
-    for (int j = 0; j < GEMM_TILES; j++) wcur[j] = iters > 0 ? ldg_stream_u4(wbase + (size_t)(8 * j) * a.K) : make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < GEMM_TILES; j++) gm_cp16(dst + j * 512, wb + (size_t)(8 * j) * a.K);
+        }
+        gm_cp_commit();
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < GEMM_STAGES; s0++) issue(blockIdx.x, s0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -110,6 +127,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
         rs_g8 = row_rs[g + 8];
     }
 
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int tile = item % tiles, split = item / tiles;
+    const int n0 = tile * GEMM_NT;
+    const int kw0 = split * KS + warp * BG_KI;
     float acc[GEMM_TILES][4];
 #pragma unroll
     for (int j = 0; j < GEMM_TILES; j++)
@@ -120,11 +141,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
     const float *x_g8 = a.X + (size_t)(g + 8) * a.ldx + kw0 + 8 * t;
 
     for (int it = 0; it < iters; it++) {
-        uint4 wnext[GEMM_TILES];
-        if (it + 1 < iters) {
-#pragma unroll
-            for (int j = 0; j < GEMM_TILES; j++) wnext[j] = ldg_stream_u4(wbase + (size_t)(8 * j) * a.K + (it + 1) * KSTEP);
-        }
         const int koff = it * KSTEP;
         float xs[2][8];
         {
@@ -167,16 +183,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
             af[h][2] = pack_bf16(xs[0][4 * h + 2], xs[0][4 * h + 3]);
             af[h][3] = pack_bf16(xs[1][4 * h + 2], xs[1][4 * h + 3]);
         }
+        // this iteration's weights have landed; pull them into registers and hand the stage to iteration it + STAGES
+        gm_cp_wait<GEMM_STAGES - 1>();
+        uint4 wcur[GEMM_TILES];
+        {
+            const uint8_t *src = gemm_smem + (warp * GEMM_STAGES + (it % GEMM_STAGES)) * GEMM_STAGE_BYTES + lane * 16;
+#pragma unroll
+            for (int j = 0; j < GEMM_TILES; j++) wcur[j] = *reinterpret_cast<const uint4 *>(src + j * 512);
+        }
+        issue(item, it + GEMM_STAGES);
 #pragma unroll
         for (int j = 0; j < GEMM_TILES; j++) {
             mma_bf16(acc[j], af[0][0], af[0][1], af[0][2], af[0][3], wcur[j].x, wcur[j].y);
             mma_bf16(acc[j], af[1][0], af[1][1], af[1][2], af[1][3], wcur[j].z, wcur[j].w);
         }
-        if (it + 1 < iters) {
-#pragma unroll
-            for (int j = 0; j < GEMM_TILES; j++) wcur[j] = wnext[j];
-        }
     }
+    gm_cp_wait<0>();
+    __syncthreads();   // every warp is done with its ring: the reduction buffer below aliases it
 
     // ---- cross-warp reduction (fixed order) ----
     float *myred = red + warp * GEMM_M * GEMM_RED_LD;
@@ -193,6 +216,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
         float4 p = *reinterpret_cast<const float4 *>(red + (w * GEMM_M + m) * GEMM_RED_LD + nn);
         v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
     }
+    __syncthreads();   // the reduction buffer is consumed: the ring is free again
+    // the first iterations of my next item fly during the split-K tail and the epilogue of this one
+#pragma unroll
+    for (int s0 = 0; s0 < GEMM_STAGES; s0++) issue(item + (int)gridDim.x, s0);
 
     if (a.splits > 1) {
         float *wst = a.ws + ((size_t)tile * a.splits) * (GEMM_M * GEMM_NT);
@@ -205,7 +232,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
             if (s_is_last) a.counters[tile] = 0u;
         }
         __syncthreads();
-        if (!s_is_last) return;
+        if (!s_is_last) continue;       // CTA-uniform; the barrier above also protects `red` for the next item
         __threadfence();
         v = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < a.splits; s++) {
@@ -221,6 +248,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
         float4 r4 = *reinterpret_cast<const float4 *>(a.resid + (size_t)m * a.ld_resid + n);
         v.x = bf16r(r4.x + v.x); v.y = bf16r(r4.y + v.y); v.z = bf16r(r4.z + v.z); v.w = bf16r(r4.w + v.w);
     }
+    if (EPI == BEPI_SWIGLU) {
+        // lanes c (x1, columns 4c..4c+3 of the tile's first half) and c + 8 (the matching x3 columns) of the same row
+        float4 o;
+        o.x = __shfl_xor_sync(0xffffffffu, v.x, 8); o.y = __shfl_xor_sync(0xffffffffu, v.y, 8);
+        o.z = __shfl_xor_sync(0xffffffffu, v.z, 8); o.w = __shfl_xor_sync(0xffffffffu, v.w, 8);
+        if (nn < 32) {
+            float4 hq;
+            hq.x = bf16r(bf16r(v.x / (1.0f + expf(-v.x))) * o.x); hq.y = bf16r(bf16r(v.y / (1.0f + expf(-v.y))) * o.y);
+            hq.z = bf16r(bf16r(v.z / (1.0f + expf(-v.z))) * o.z); hq.w = bf16r(bf16r(v.w / (1.0f + expf(-v.w))) * o.w);
+            *reinterpret_cast<float4 *>(a.Y + (size_t)m * a.ldy + tile * 32 + nn) = hq;
+        }
+    } else
     *reinterpret_cast<float4 *>(a.Y + (size_t)m * a.ldy + n) = v;
     if (a.stats_out != nullptr) {
         float s = v.x + v.y + v.z + v.w;
@@ -233,6 +272,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
         for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         if ((tid & 15) == 0) a.stats_out[tile * GEMM_M + m] = make_float2(mean, q);
     }
+    __syncthreads();   // `red` / `s_is_last` are reused by the next item
+  }
 }
 
 int launch_skinny_gemm_bf16(int pro, int epi, const Bf16GemmArgs &a, cudaStream_t stream);

@@ -38,7 +38,9 @@ class ChameleonEngine:
                 one, zero = torch.ones(hd, device=self.device), torch.zeros(hd, device=self.device)
                 qn = [one, zero, one.clone(), zero.clone()]
             w13 = bf(state[p + "feed_forward.w13.weight"])
-            self.ffn_hidden = w13.shape[0] // 2
+            self.ffn_hidden = F = w13.shape[0] // 2
+            # interleave per 64-row tile: 32 rows of w1 (x1), then the matching 32 rows of w3 (x3) -- see wmar_b200.h
+            w13 = torch.stack((w13[:F].view(F // 32, 32, -1), w13[F:].view(F // 32, 32, -1)), dim=1).reshape(2 * F, -1).contiguous()
             tensors += [f32(state[p + "attention_norm.weight"]), bf(state[p + "attention.wqkv.weight"]), *qn,
                         bf(state[p + "attention.wo.weight"]), f32(state[p + "ffn_norm.weight"]), w13,
                         bf(state[p + "feed_forward.w2.weight"])]
