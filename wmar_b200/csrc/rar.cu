@@ -15,6 +15,7 @@
 //     head:  (scale, shift) = Linear(SiLU(c_i)) ; logits = (LN_noaffine(x)(1+scale)+shift) Wlm^T + b  rar.py:131-134
 //     pass i >= 1 samples image token i-1:  u + (c - u) * cfg -> +delta on green(ids) -> /T -> softmax -> multinomial
 // KV cache: fp32 [layer][row16][head][seq+2][hd], one contiguous stream per (layer,row,head).
+#include <algorithm>
 #include <vector>
 
 #include "gemm.cuh"
@@ -66,6 +67,10 @@ struct wmar_rar {
     size_t graph_smem;
     int graph_B;
     int s_ada, s_qkv, s_proj, s_fc1, s_fc2, s_hada, s_lm;
+    // the adaLN modulation GEMMs depend only on the conditioning, not on x: they run on a forked branch of the step
+    // graph, off the critical path, with their own split-K workspace; mod holds one [16][6d] block per layer
+    float *ws_side;
+    unsigned *counters_side;
     int launches_per_pass;
 };
 
@@ -285,7 +290,24 @@ void rar_free_graph(wmar_rar *g) {
     g->graph = nullptr;
 }
 
-int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s) {
+// events of the fork / join edges captured into the step graph (capture-time only objects, shared by all handles)
+cudaEvent_t g_fork_event() {
+    static cudaEvent_t e = nullptr;
+    if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+}
+cudaEvent_t g_layer_event(int l) {
+    static std::vector<cudaEvent_t> ev;
+    while ((int)ev.size() <= l) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        ev.push_back(e);
+    }
+    return ev[l];
+}
+
+// `side`: second capturing stream for the forked adaLN branch (null: everything in order on `s`)
+int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cudaStream_t side) {
     const wmar_rar_config &c = g->cfg;
     const int d = g->d, H = c.n_head, V = c.codebook_size, mlp = c.mlp;
     const int stat_tiles = d / 64;
@@ -295,18 +317,40 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s) {
                                         g->stats);
     WMAR_LAUNCH_CHECK();
     launches++;
+    // ---- forked branch: all adaLN modulations of this pass (they read SiLU(c) only) ----
+    const bool capturing = side != nullptr;
+    cudaStream_t ms = capturing ? side : s;
+    const size_t mod_ld = (size_t)16 * 6 * d;
+    if (capturing) {
+        WMAR_CUDA_CHECK(cudaEventRecord(g_fork_event(), s));
+        WMAR_CUDA_CHECK(cudaStreamWaitEvent(side, g_fork_event(), 0));
+    }
     for (int l = 0; l < c.n_layer; l++) {
         const RarLayer &L = g->layers[l];
         GemmArgs m{};
-        m.ws = g->ws; m.counters = g->counters;
-        m.X = g->csilu; m.ldx = d; m.W = L.wada; m.bias = L.bada; m.Y = g->mod; m.ldy = 6 * d; m.N = 6 * d; m.K = d;
+        m.ws = g->ws_side; m.counters = g->counters_side;
+        m.X = g->csilu; m.ldx = d; m.W = L.wada; m.bias = L.bada; m.Y = g->mod + l * mod_ld; m.ldy = 6 * d; m.N = 6 * d; m.K = d;
         m.splits = g->s_ada;
-        if ((rc = launch_skinny_gemm(PRO_NONE, EPI_STORE, m, s))) return rc;
+        if ((rc = launch_skinny_gemm(PRO_NONE, EPI_STORE, m, ms))) return rc;
+        if (capturing) WMAR_CUDA_CHECK(cudaEventRecord(g_layer_event(l), side));
+    }
+    {
+        GemmArgs hm{};
+        hm.ws = g->ws_side; hm.counters = g->counters_side;
+        hm.X = g->csilu; hm.ldx = d; hm.W = g->whada; hm.bias = g->bhada; hm.Y = g->hmod; hm.ldy = 2 * d; hm.N = 2 * d; hm.K = d;
+        hm.splits = g->s_hada;
+        if ((rc = launch_skinny_gemm(PRO_NONE, EPI_STORE, hm, ms))) return rc;
+        if (capturing) WMAR_CUDA_CHECK(cudaEventRecord(g_layer_event(c.n_layer), side));
+    }
+    for (int l = 0; l < c.n_layer; l++) {
+        const RarLayer &L = g->layers[l];
+        float *mod = g->mod + l * mod_ld;
+        if (capturing) WMAR_CUDA_CHECK(cudaStreamWaitEvent(s, g_layer_event(l), 0));
         GemmArgs a{};
         a.ws = g->ws; a.counters = g->counters; a.eps = 1e-6f;
         a.X = g->x; a.ldx = d; a.W = L.wqkv; a.bias = L.bqkv; a.Y = g->qkv; a.ldy = 3 * d; a.N = 3 * d; a.K = d;
         a.splits = g->s_qkv; a.ln_g = L.n1_g; a.ln_b = L.n1_b; a.stats_in = g->stats; a.n_stat_tiles = stat_tiles;
-        a.mod_shift = g->mod; a.mod_scale = g->mod + d; a.ld_mod = 6 * d;
+        a.mod_shift = mod; a.mod_scale = mod + d; a.ld_mod = 6 * d;
         if ((rc = launch_skinny_gemm(PRO_ADALN, EPI_STORE, a, s))) return rc;
         rar_attn_kernel<<<dim3(H, 2 * B), RAR_ATT_THREADS, 0, s>>>(g->qkv, d, H, g->hd, g->T, L.qn_g, L.qn_b, L.kn_g, L.kn_b,
                                                                   g->kcache, g->vcache, l, g->pos, g->y);
@@ -314,28 +358,24 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s) {
         GemmArgs p{};
         p.ws = g->ws; p.counters = g->counters;
         p.X = g->y; p.ldx = d; p.W = L.wproj; p.bias = L.bproj; p.Y = g->x; p.ldy = d; p.N = d; p.K = d;
-        p.splits = g->s_proj; p.resid = g->x; p.ld_resid = d; p.gate = g->mod + 2 * d; p.ld_gate = 6 * d;
+        p.splits = g->s_proj; p.resid = g->x; p.ld_resid = d; p.gate = mod + 2 * d; p.ld_gate = 6 * d;
         p.stats_out = g->stats;
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_GATE_RESID, p, s))) return rc;
         GemmArgs f{};
         f.ws = g->ws; f.counters = g->counters; f.eps = 1e-6f;
         f.X = g->x; f.ldx = d; f.W = L.w1; f.bias = L.b1; f.Y = g->hbuf; f.ldy = mlp; f.N = mlp; f.K = d;
         f.splits = g->s_fc1; f.ln_g = L.n2_g; f.ln_b = L.n2_b; f.stats_in = g->stats; f.n_stat_tiles = stat_tiles;
-        f.mod_shift = g->mod + 3 * d; f.mod_scale = g->mod + 4 * d; f.ld_mod = 6 * d;
+        f.mod_shift = mod + 3 * d; f.mod_scale = mod + 4 * d; f.ld_mod = 6 * d;
         if ((rc = launch_skinny_gemm(PRO_ADALN, EPI_GELU, f, s))) return rc;
         GemmArgs o{};
         o.ws = g->ws; o.counters = g->counters;
         o.X = g->hbuf; o.ldx = mlp; o.W = L.w2; o.bias = L.b2; o.Y = g->x; o.ldy = d; o.N = d; o.K = mlp;
-        o.splits = g->s_fc2; o.resid = g->x; o.ld_resid = d; o.gate = g->mod + 5 * d; o.ld_gate = 6 * d;
+        o.splits = g->s_fc2; o.resid = g->x; o.ld_resid = d; o.gate = mod + 5 * d; o.ld_gate = 6 * d;
         o.stats_out = g->stats;
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_GATE_RESID, o, s))) return rc;
         launches += 6;
     }
-    GemmArgs hm{};
-    hm.ws = g->ws; hm.counters = g->counters;
-    hm.X = g->csilu; hm.ldx = d; hm.W = g->whada; hm.bias = g->bhada; hm.Y = g->hmod; hm.ldy = 2 * d; hm.N = 2 * d; hm.K = d;
-    hm.splits = g->s_hada;
-    if ((rc = launch_skinny_gemm(PRO_NONE, EPI_STORE, hm, s))) return rc;
+    if (capturing) WMAR_CUDA_CHECK(cudaStreamWaitEvent(s, g_layer_event(c.n_layer), 0));   // joins the forked branch
     GemmArgs lm{};
     lm.ws = g->ws; lm.counters = g->counters; lm.eps = 1e-6f;
     lm.X = g->x; lm.ldx = d; lm.W = g->wlm; lm.bias = g->blm; lm.Y = g->logits; lm.ldy = V; lm.N = V; lm.K = d;
@@ -406,7 +446,13 @@ int wmar_rar_create(const wmar_rar_config *cfg, const void *const *d_weights, in
     const size_t kv_elems = (size_t)cfg->n_layer * 16 * d * g->T;
     WMAR_CUDA_CHECK(cudaMalloc(&g->x, sizeof(float) * 16 * d));
     WMAR_CUDA_CHECK(cudaMalloc(&g->csilu, sizeof(float) * 16 * d));
-    WMAR_CUDA_CHECK(cudaMalloc(&g->mod, sizeof(float) * 16 * 6 * d));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->mod, sizeof(float) * 16 * 6 * d * (size_t)cfg->n_layer));
+    {
+        const size_t side_ws = std::max(gemm_ws_floats(6 * d, d, g->s_ada, g->n_sms), gemm_ws_floats(2 * d, d, g->s_hada, g->n_sms));
+        WMAR_CUDA_CHECK(cudaMalloc(&g->ws_side, sizeof(float) * (side_ws ? side_ws : 1)));
+        WMAR_CUDA_CHECK(cudaMalloc(&g->counters_side, sizeof(unsigned) * (6 * d / GEMM_NT)));
+        WMAR_CUDA_CHECK(cudaMemset(g->counters_side, 0, sizeof(unsigned) * (6 * d / GEMM_NT)));
+    }
     WMAR_CUDA_CHECK(cudaMalloc(&g->qkv, sizeof(float) * 16 * 3 * d));
     WMAR_CUDA_CHECK(cudaMalloc(&g->y, sizeof(float) * 16 * d));
     WMAR_CUDA_CHECK(cudaMalloc(&g->hbuf, sizeof(float) * 16 * mlp));
@@ -428,7 +474,7 @@ int wmar_rar_create(const wmar_rar_config *cfg, const void *const *d_weights, in
     WMAR_CUDA_CHECK(cudaMemset(g->counters, 0, sizeof(unsigned) * max_tiles));
     WMAR_CUDA_CHECK(cudaMemset(g->x, 0, sizeof(float) * 16 * d));
     WMAR_CUDA_CHECK(cudaMemset(g->csilu, 0, sizeof(float) * 16 * d));
-    WMAR_CUDA_CHECK(cudaMemset(g->mod, 0, sizeof(float) * 16 * 6 * d));
+    WMAR_CUDA_CHECK(cudaMemset(g->mod, 0, sizeof(float) * 16 * 6 * d * (size_t)cfg->n_layer));
     WMAR_CUDA_CHECK(cudaMemset(g->qkv, 0, sizeof(float) * 16 * 3 * d));
     WMAR_CUDA_CHECK(cudaMemset(g->y, 0, sizeof(float) * 16 * d));
     WMAR_CUDA_CHECK(cudaMemset(g->hbuf, 0, sizeof(float) * 16 * mlp));
@@ -445,6 +491,7 @@ void wmar_rar_destroy(wmar_rar *g) {
     if (!g) return;
     cudaDeviceSynchronize();
     rar_free_graph(g);
+    cudaFree(g->ws_side); cudaFree(g->counters_side);
     cudaFree(g->x); cudaFree(g->csilu); cudaFree(g->mod); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->hbuf);
     cudaFree(g->hmod); cudaFree(g->logits); cudaFree(g->guided); cudaFree(g->kcache); cudaFree(g->vcache); cudaFree(g->ws);
     cudaFree(g->stats); cudaFree(g->counters); cudaFree(g->ids); cudaFree(g->pos); cudaFree(g->d_call);
@@ -485,9 +532,12 @@ int wmar_rar_sample(wmar_rar *g, const wmar_wm_params *wm, const wmar_sample_par
         cudaStream_t cs;
         WMAR_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         WMAR_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        rc = rar_enqueue_pass(g, (int)B, smem, cs);
+        cudaStream_t side;
+        WMAR_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        rc = rar_enqueue_pass(g, (int)B, smem, cs, side);
         cudaError_t e = cudaStreamEndCapture(cs, &g->graph);
         cudaStreamDestroy(cs);
+        cudaStreamDestroy(side);
         if (rc) { if (g->graph) cudaGraphDestroy(g->graph); g->graph = nullptr; return rc; }
         if (e != cudaSuccess) return set_error(WMAR_ERR_CUDA, "cudaStreamEndCapture: %s%s", cudaGetErrorString(e));
         WMAR_CUDA_CHECK(cudaGraphInstantiate(&g->exec, g->graph, 0));
