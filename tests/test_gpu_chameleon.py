@@ -131,3 +131,33 @@ def test_chameleon_engine_sampling_with_reference_noise_and_watermark():
         np.testing.assert_array_equal(ids_c[:, s].numpy(), want.numpy())
     frac = np.isin(ids_c.numpy(), green).mean()
     assert frac > 0.25                            # the bias is visible
+
+
+def test_chameleon_wrapper_roundtrip_small():
+    """ChameleonARMMWrapper at reduced shapes: sample -> codes_to_images -> images_to_codes -> detect keep the reference's
+    shapes / ranges / vocab conventions (chameleon_wrapper.py:139-186)."""
+    from wmar_b200.models.chameleon_wrapper import (BEGIN_IMAGE, IMAGE_TOKEN_HI, IMAGE_TOKEN_LO, ChameleonARMMWrapper)
+    from wmar_b200.watermarking import create_watermarker_from_string
+    cfg = dict(vocab_size=16384, dim=256, n_layers=2, n_heads=2, n_kv_heads=2, ffn_hidden=384, norm_eps=1e-5, rope_theta=10000.0,
+               qk_normalization=True)
+    vq = dict(ch=128, out_ch=3, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(), in_channels=3, resolution=32,
+              z_channels=256, n_embed=8192, embed_dim=256)
+    m = ChameleonARMMWrapper(model_cfg=cfg, vq_cfg=vq, max_batch=2, image_tokens_per_image=256,
+                             tokenize=lambda p: [16384 - 1 - (len(w) % 7) for w in p.split()])
+    assert m.get_total_vocab_size() == 16384 and m.codes_size == 16 and m.image_size == 32
+    rows = m.prompt_rows(["a red bus", "two cats on a couch"])
+    assert len(rows) == 6 and all(r[-1] == BEGIN_IMAGE for r in rows) and rows[2] == [0, BEGIN_IMAGE] and rows[4] == [0, BEGIN_IMAGE]
+    wm = create_watermarker_from_string(m.get_vq(), m.get_total_vocab_size(), "fixed-stratifiedrand-h=0-d=4.0-g=0.25", m.device)
+    m.set_watermarker(wm)
+    torch.manual_seed(0)
+    cond = [(0, "a red bus"), (1, "two cats on a couch"), (2, "a dog")]          # 3 prompts, max_batch 2 -> two engine calls
+    codes = m.sample(cond, {"temperature": 0.9, "top_p": 0.9}, apply_watermark=True)
+    assert codes.shape == (3, 256) and int(codes.min()) >= IMAGE_TOKEN_LO and int(codes.max()) < IMAGE_TOKEN_HI
+    imgs = m.codes_to_images(codes)
+    assert imgs.shape == (3, 3, 32, 32) and float(imgs.min()) >= -1.0 and float(imgs.max()) <= 1.0
+    back = m.images_to_codes(imgs)
+    assert back.shape == codes.shape and int(back.min()) >= IMAGE_TOKEN_LO and int(back.max()) < IMAGE_TOKEN_HI
+    p_wm = wm.detect(codes)
+    codes0 = m.sample(cond, {"temperature": 0.9, "top_p": 0.9}, apply_watermark=False)
+    p_0 = wm.detect(codes0)
+    assert float(p_wm.max()) < 1e-6 < float(p_0.min())                          # delta 4: the watermark is unmistakable

@@ -130,15 +130,18 @@ def main(argv=None):
     torch.manual_seed(seed)
     torch.cuda.manual_seed_all(seed)
 
-    from wmar_b200.models import RarARMMWrapper, TamingARMMWrapper
+    from wmar_b200.models import ChameleonARMMWrapper, RarARMMWrapper, TamingARMMWrapper
     from wmar_b200.models.state import update_weights
     from wmar_b200.watermarking import GentimeWatermark, SeedStrategy, SplitStrategy
     if args.model == "taming":
         model = TamingARMMWrapper(args.modelpath, device=device, max_batch=min(16, args.batch_size))
     elif args.model == "rar":
         model = RarARMMWrapper(args.modelpath, device=device, max_batch=min(8, args.batch_size))
+    elif args.model == "chameleon7b":
+        # no checkpoint / text tokenizer offline: Anole-7B shapes with seeded random weights (wrapper docstring)
+        model = ChameleonARMMWrapper(args.modelpath, device=device, max_batch=min(5, args.batch_size), seed=args.seed)
     else:
-        raise ValueError(f"Model {args.model} not supported by wmar_b200 yet")
+        raise ValueError(f"Model {args.model} not supported by wmar_b200")
     patched = False
     if args.encoder_ft_ckpt not in (None, "none"):
         update_weights(model.get_image_tokenizer().encoder, args.encoder_ft_ckpt)
