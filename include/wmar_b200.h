@@ -207,7 +207,7 @@ typedef struct wmar_cham_config {
     int vocab_size, dim, n_layer, n_head, n_kv_head;
     int ffn_hidden;       /* F: the FeedForward hidden size after the multiple_of rounding (11008 for 7B)          */
     int max_seq;          /* cache positions per row: longest prompt + generated tokens                            */
-    int max_batch;        /* images per call, <= 5 (3B guided rows <= 16)                                          */
+    int max_batch;        /* images per call, <= 8 (n_groups * B guided rows <= 16)                                */
     int image_token_lo, image_token_hi; /* allowed ids [lo, hi): vocab.image_tokens (4..8195 for Chameleon)        */
     float norm_eps, rope_theta;
     int qk_norm;          /* ModelArgs.qk_normalization                                                            */
@@ -217,15 +217,17 @@ typedef struct wmar_cham wmar_cham;
 
 int wmar_cham_create(const wmar_cham_config *cfg, const void *const *d_weights, int n_weights, wmar_cham **out);
 void wmar_cham_destroy(wmar_cham *g);
-/* d_prompts int64 [3B][max_prompt] (rows: B full-conditioned, B image-conditioned, B unconditioned prompts, each ending
- * in <boi>, left-aligned), d_prompt_len int32 [3B], p_max = the longest prompt.  d_noise fp32 [steps][B][V] (the
+/* d_prompts int64 [n_groups*B][max_prompt] (rows: B full-conditioned, B image-conditioned, B unconditioned prompts, each
+ * ending in <boi>, left-aligned), d_prompt_len int32 [n_groups*B], p_max = the longest prompt.  n_groups = 3, or 2 when
+ * the image-conditioned rows equal the unconditioned ones (text-only prompts: the rows are then [full | unconditioned]
+ * and the guidance reads the unconditioned logits for both; bit-identical to the 3-group result, 8 images per call).  d_noise fp32 [steps][B][V] (the
  * Exp(1) draws of torch.multinomial over the full vocabulary) or NULL; d_out_ids int64 [B][steps];
  * d_out_logits (optional) fp32 [steps][B][hi-lo] = the mixed logits of the image-token window before the watermark. */
 int wmar_cham_sample(wmar_cham *g, const wmar_wm_params *wm, const wmar_sample_params *sp, const int64_t *d_prompts,
-                     const int32_t *d_prompt_len, int64_t max_prompt, int64_t p_max, int64_t B, float guidance_text,
-                     float guidance_image, int64_t steps, const float *d_noise, int64_t *d_out_ids, float *d_out_logits,
-                     void *stream);
-double wmar_cham_algorithmic_bytes(const wmar_cham *g, int64_t B, int64_t p_max, int64_t steps);
+                     const int32_t *d_prompt_len, int64_t max_prompt, int64_t p_max, int64_t B, int n_groups,
+                     float guidance_text, float guidance_image, int64_t steps, const float *d_noise, int64_t *d_out_ids,
+                     float *d_out_logits, void *stream);
+double wmar_cham_algorithmic_bytes(const wmar_cham *g, int64_t B, int n_groups, int64_t p_max, int64_t steps);
 int wmar_cham_launches_per_pass(const wmar_cham *g);
 /* The logits-processor + token-selector operator of ImageDecoder on GIVEN logits (chameleon.py:312-346, generation.py:
  * 86-97): d_logits3 fp32 [3B][V] (full | image-conditioned | unconditioned rows) -> mixed = u + s_img (i-u) + s_txt (f-i)

@@ -2,7 +2,7 @@
 
     python scripts/bench_workloads.py rar        # RAR-XL 256x256, greenlist watermark, 8 images / GPU (16 guided rows)
     python scripts/bench_workloads.py detect     # detection only: VQGAN encode + z-score on synthetic 256x256 images
-    python scripts/bench_workloads.py anole      # Anole-7B text -> image 512x512, watermark on, 5 images / GPU
+    python scripts/bench_workloads.py anole      # Anole-7B text -> image 512x512, watermark on, 8 images / GPU (16 guided rows)
 
 Each prints one JSON line (images/s per GPU, phase times from CUDA events, roofline of the dominant phase against
 MEASURED_PEAKS.json).  Synthetic data, seeded random-init weights at the reference's shapes.  Single GPU: the path shards
@@ -89,14 +89,15 @@ def detect():
 def anole():
     from wmar_b200.models.chameleon_wrapper import ChameleonARMMWrapper
     from wmar_b200.watermarking import create_watermarker_from_string
-    B = 5
+    B = 8    # text-only prompts: the image-conditioned rows equal the unconditioned ones -> 2 x 8 = 16 guided rows
     m = ChameleonARMMWrapper(max_batch=B)
     wm = create_watermarker_from_string(m.get_vq(), m.get_total_vocab_size(), "fixed-stratifiedrand-h=0-d=2.0-g=0.25", m.device)
     m.set_watermarker(wm)
     torch.manual_seed(1)
     prompts = ["a photo of a red bus parked next to a building on a sunny day", "two cats sleeping on a couch",
                "a plate of food with broccoli and rice on a wooden table", "a man riding a wave on a surfboard",
-               "a kitchen with a stove a sink and a window"]
+               "a kitchen with a stove a sink and a window", "a group of people flying kites in a park",
+               "a close up of a pizza on a table", "a train traveling down tracks next to a forest"]
     cond = list(enumerate(prompts))
     ms_s, codes = timed(lambda: m.sample(cond, {"temperature": 0.9, "top_p": 0.9}, apply_watermark=True), reps=1, warmup=1)
     ms_d, imgs = timed(lambda: m.codes_to_images(codes), reps=2)
@@ -104,7 +105,7 @@ def anole():
     p_max = max(len(r) for r in m.prompt_rows(prompts))
     by = m._eng.algorithmic_bytes(B, p_max, 1024)
     pk = float(peaks().get("hbm_gbs", 6650.0))
-    return {"workload": "anole_7b_512_B5_cfg3.0_1.2_T0.9_p0.9_wm_fixed_h0_d2_g0.25", "images_per_s_per_gpu": B / ((ms_s + ms_d + ms_t) * 1e-3),
+    return {"workload": "anole_7b_512_B8_cfg3.0_1.2_T0.9_p0.9_wm_fixed_h0_d2_g0.25", "images_per_s_per_gpu": B / ((ms_s + ms_d + ms_t) * 1e-3),
             "phase_ms": {"sample": ms_s, "vqgan_decode_512": ms_d, "detect": ms_t},
             "roofline": {"bound": "hbm", "kernel": "Anole-7B decode loop (prompt + 1023 passes, bf16 weights)",
                          "achieved": by / ms_s / 1e6, "peak": pk, "unit": "GB/s", "frac": by / ms_s / 1e6 / pk, "algorithmic_bytes": by},

@@ -15,7 +15,7 @@ def main():
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     c = ANOLE_7B_CFG
     w = chameleon_state(c, seed=0, device="cuda")
-    eng = ChameleonEngine(w, c["n_layers"], c["n_heads"], c["n_kv_heads"], max_seq=1100, max_batch=5)
+    eng = ChameleonEngine(w, c["n_layers"], c["n_heads"], c["n_kv_heads"], max_seq=1100, max_batch=8)
     del w
     torch.manual_seed(0)
     full = [[0] + torch.randint(16384, 65536, (12 + 3 * b,)).tolist() + [8710, 8197] for b in range(B)]

@@ -89,9 +89,9 @@ EXPORTS = {
                                         ctypes.POINTER(c_voidp)]),
     "wmar_cham_destroy": (None, [c_voidp]),
     "wmar_cham_sample": (ctypes.c_int, [c_voidp, ctypes.POINTER(WmParams), ctypes.POINTER(SampleParams), c_voidp, c_voidp,
-                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_int64, c_voidp, c_voidp, c_voidp, c_voidp]),
-    "wmar_cham_algorithmic_bytes": (ctypes.c_double, [c_voidp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]),
+    "wmar_cham_algorithmic_bytes": (ctypes.c_double, [c_voidp, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_int64]),
     "wmar_cham_launches_per_pass": (ctypes.c_int, [c_voidp]),
     "wmar_cham_select": (ctypes.c_int, [ctypes.POINTER(WmParams), ctypes.POINTER(SampleParams), c_voidp, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_float,

@@ -44,6 +44,8 @@ struct ChamCall {
     float *out_logits;          // [steps][B][W] mixed logits of the image-token window (before the watermark) or null
     float s_txt, s_img;
     int B, steps, max_prompt, p_max;
+    int n_groups;   // 3: full | image-conditioned | unconditioned rows; 2: the image-conditioned rows ARE the unconditioned
+                    // ones (text-only prompts: both reduce to <s> <boi>, chameleon.py:351-372), computed once
 };
 
 struct ChamLayer {
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) cham_embed_kernel(const ChamCall *cp, con
     const int r = blockIdx.x, i = *pass, B = cp->B;
     int p = -1;
     long long tok = 0;
-    if (r < 3 * B) {
+    if (r < cp->n_groups * B) {
         const int P = cp->prompt_len[r];
         p = i - (cp->p_max - P);
         if (p >= 0) {
@@ -303,7 +305,8 @@ __global__ void __launch_bounds__(256) cham_guide_kernel(const ChamCall *cp, con
     const int s = i - (cp->p_max - 1);
     if (s < 0 || s >= cp->steps) return;
     const int B = cp->B;
-    const float *lf = logits + (size_t)b * V + lo, *li = logits + (size_t)(B + b) * V + lo, *lu = logits + (size_t)(2 * B + b) * V + lo;
+    const float *lf = logits + (size_t)b * V + lo, *li = logits + (size_t)(B + b) * V + lo,
+                *lu = logits + (size_t)((cp->n_groups - 1) * B + b) * V + lo;   // 2 groups: li == lu
     const float s_txt = cp->s_txt, s_img = cp->s_img;
     for (int v = threadIdx.x; v < W; v += blockDim.x) {
         const float u = lu[v], im = li[v], f = lf[v];
@@ -361,7 +364,7 @@ void cham_free_graph(wmar_cham *g) {
     g->graph = nullptr;
 }
 
-int cham_enqueue_pass(wmar_cham *g, int B, size_t sample_smem, cudaStream_t s) {
+int cham_enqueue_pass(wmar_cham *g, int B, int n_groups, size_t sample_smem, cudaStream_t s) {
     const wmar_cham_config &c = g->cfg;
     const int d = g->d, H = c.n_head, Hkv = c.n_kv_head, V = c.vocab_size, F = g->F;
     const int qkv_n = (H + 2 * Hkv) * g->hd;
@@ -379,7 +382,7 @@ int cham_enqueue_pass(wmar_cham *g, int B, size_t sample_smem, cudaStream_t s) {
         if ((rc = launch_skinny_gemm_bf16(BPRO_RMS, BEPI_STORE, a, s))) return rc;
         {
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)H, (unsigned)(3 * B), 1);
+            cfg.gridDim = dim3((unsigned)H, (unsigned)(n_groups * B), 1);
             cfg.blockDim = dim3(CH_ATT_THREADS, 1, 1);
             cfg.stream = s;
             cudaLaunchAttribute attr[1];
@@ -441,7 +444,7 @@ int wmar_cham_create(const wmar_cham_config *cfg, const void *const *d_weights, 
     WMAR_REQUIRE(cfg->dim % 64 == 0 && cfg->vocab_size % 64 == 0 && cfg->ffn_hidden % 64 == 0, "dim, vocab and ffn_hidden must be multiples of 64");
     WMAR_REQUIRE(cfg->ffn_hidden % 32 == 0, "ffn_hidden must be a multiple of 32 (w13 row interleave)");
     WMAR_REQUIRE(cfg->max_seq >= 2 && cfg->max_seq <= 4096, "max_seq must be in [2,4096]");
-    WMAR_REQUIRE(cfg->max_batch >= 1 && 3 * cfg->max_batch <= 16, "max_batch must be in [1,5] (3B guided rows <= 16)");
+    WMAR_REQUIRE(cfg->max_batch >= 1 && 2 * cfg->max_batch <= 16, "max_batch must be in [1,8] (2B or 3B guided rows <= 16)");
     WMAR_REQUIRE(cfg->image_token_lo >= 0 && cfg->image_token_hi > cfg->image_token_lo && cfg->image_token_hi <= cfg->vocab_size,
                  "bad image token range");
     WMAR_REQUIRE(n_weights == 1 + 10 * cfg->n_layer + 2, "weight table has the wrong number of entries");
@@ -527,11 +530,12 @@ void wmar_cham_destroy(wmar_cham *g) {
 }
 
 int wmar_cham_sample(wmar_cham *g, const wmar_wm_params *wm, const wmar_sample_params *sp, const int64_t *d_prompts,
-                     const int32_t *d_prompt_len, int64_t max_prompt, int64_t p_max, int64_t B, float guidance_text,
+                     const int32_t *d_prompt_len, int64_t max_prompt, int64_t p_max, int64_t B, int n_groups, float guidance_text,
                      float guidance_image, int64_t steps, const float *d_noise, int64_t *d_out_ids, float *d_out_logits,
                      void *stream) {
     WMAR_REQUIRE(g != nullptr && sp != nullptr && d_prompts != nullptr && d_prompt_len != nullptr && d_out_ids != nullptr, "NULL argument");
-    WMAR_REQUIRE(B >= 1 && B <= g->cfg.max_batch, "batch exceeds max_batch");
+    WMAR_REQUIRE(n_groups == 2 || n_groups == 3, "n_groups must be 2 (text-only prompts) or 3");
+    WMAR_REQUIRE(B >= 1 && B <= g->cfg.max_batch && n_groups * B <= 16, "batch exceeds max_batch or 16 guided rows");
     WMAR_REQUIRE(p_max >= 1 && p_max <= max_prompt, "p_max (longest prompt) must be in [1, max_prompt]");
     WMAR_REQUIRE(steps >= 1 && p_max + steps <= g->cfg.max_seq, "prompt + steps exceeds max_seq");
     cudaStream_t s = as_stream(stream);
@@ -563,24 +567,25 @@ int wmar_cham_sample(wmar_cham *g, const wmar_wm_params *wm, const wmar_sample_p
     g->h_call->steps = (int)steps;
     g->h_call->max_prompt = (int)max_prompt;
     g->h_call->p_max = (int)p_max;
+    g->h_call->n_groups = n_groups;
     WMAR_CUDA_CHECK(cudaMemcpyAsync(g->d_call, g->h_call, sizeof(ChamCall), cudaMemcpyHostToDevice, s));
     WMAR_CUDA_CHECK(cudaEventRecord(g->call_done, s));
     g->call_pending = true;
 
-    if (g->exec == nullptr || g->graph_smem != smem || g->graph_B != (int)B) {
+    if (g->exec == nullptr || g->graph_smem != smem || g->graph_B != (int)B * 4 + n_groups) {
         cham_free_graph(g);
         WMAR_CUDA_CHECK(cudaFuncSetAttribute(cham_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaStream_t cs;
         WMAR_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         WMAR_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        rc = cham_enqueue_pass(g, (int)B, smem, cs);
+        rc = cham_enqueue_pass(g, (int)B, n_groups, smem, cs);
         cudaError_t e = cudaStreamEndCapture(cs, &g->graph);
         cudaStreamDestroy(cs);
         if (rc) { if (g->graph) cudaGraphDestroy(g->graph); g->graph = nullptr; return rc; }
         if (e != cudaSuccess) return set_error(WMAR_ERR_CUDA, "cudaStreamEndCapture: %s%s", cudaGetErrorString(e));
         WMAR_CUDA_CHECK(cudaGraphInstantiate(&g->exec, g->graph, 0));
         g->graph_smem = smem;
-        g->graph_B = (int)B;
+        g->graph_B = (int)B * 4 + n_groups;
     }
     cham_init_kernel<<<(unsigned)B, 64, 0, s>>>(g->d_call, g->seq, g->cfg.max_seq, g->pass);
     WMAR_LAUNCH_CHECK();
@@ -592,7 +597,7 @@ int wmar_cham_sample(wmar_cham *g, const wmar_wm_params *wm, const wmar_sample_p
     return WMAR_OK;
 }
 
-double wmar_cham_algorithmic_bytes(const wmar_cham *g, int64_t B, int64_t p_max, int64_t steps) {
+double wmar_cham_algorithmic_bytes(const wmar_cham *g, int64_t B, int n_groups, int64_t p_max, int64_t steps) {
     if (!g) return 0.0;
     const double d = g->d, V = g->cfg.vocab_size, L = g->cfg.n_layer, F = g->F, H = g->cfg.n_head, Hkv = g->cfg.n_kv_head;
     // bf16 parameters streamed once per pass: per layer wqkv + wo + w13 + w2, plus the output head
@@ -600,7 +605,7 @@ double wmar_cham_algorithmic_bytes(const wmar_cham *g, int64_t B, int64_t p_max,
     double kv = 0.0;  // bf16 K and V rows read per pass and row (upper bound: every row at the longest prompt)
     const double passes = (double)(p_max + steps - 1);
     for (int64_t i = 0; i < (int64_t)passes; i++) kv += 2.0 * L * Hkv * 128.0 * (double)(i + 1);
-    return 2.0 * (P * passes + kv * 3.0 * (double)B);
+    return 2.0 * (P * passes + kv * (double)n_groups * (double)B);
 }
 
 int wmar_cham_launches_per_pass(const wmar_cham *g) { return g ? g->launches_per_pass : 0; }

@@ -12,7 +12,7 @@ class ChameleonEngine:
     device: per-row prompt prefill, 3-way classifier-free guidance, watermark, allowed-token mask, temperature, top-p,
     multinomial, token replication -- no Python per token."""
 
-    def __init__(self, state, n_layer, n_head, n_kv_head=None, image_tokens=(4, 8196), max_seq=1100, max_batch=5,
+    def __init__(self, state, n_layer, n_head, n_kv_head=None, image_tokens=(4, 8196), max_seq=1100, max_batch=8,
                  norm_eps=1e-5, rope_theta=10000.0, qk_norm=True, device="cuda"):
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -78,6 +78,12 @@ class ChameleonEngine:
         R = len(prompts3)
         assert R % 3 == 0 and R > 0
         B = R // 3
+        n_groups = 3
+        if all(list(prompts3[B + b]) == list(prompts3[2 * B + b]) for b in range(B)):
+            # text-only prompts: the image-conditioned rows are the unconditioned rows -> compute them once
+            prompts3 = list(prompts3[:B]) + list(prompts3[2 * B:])
+            n_groups, R = 2, 2 * B
+        assert n_groups * B <= 16 and B <= self.max_batch, "too many images for one call"
         p_max = max(len(p) for p in prompts3)
         assert min(len(p) for p in prompts3) >= 1
         pr = torch.zeros((R, p_max), dtype=torch.long)
@@ -95,11 +101,13 @@ class ChameleonEngine:
             noise = noise.contiguous()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().wmar_cham_sample(self.handle, ctypes.byref(wm) if wm is not None else None, ctypes.byref(sp),
-                                                   _lib.ptr(pr), _lib.ptr(plen), p_max, p_max, B, float(guidance_text),
+                                                   _lib.ptr(pr), _lib.ptr(plen), p_max, p_max, B, n_groups, float(guidance_text),
                                                    float(guidance_image), steps, _lib.ptr(noise), _lib.ptr(out),
                                                    _lib.ptr(logits), _lib.current_stream()))
         self._keepalive = (pr, plen, noise)
+        self.last_n_groups = n_groups
         return (out, logits) if return_logits else out
 
-    def algorithmic_bytes(self, B, p_max, steps):
-        return float(_lib.lib().wmar_cham_algorithmic_bytes(self.handle, B, p_max, steps))
+    def algorithmic_bytes(self, B, p_max, steps, n_groups=None):
+        n_groups = n_groups or getattr(self, "last_n_groups", 3)
+        return float(_lib.lib().wmar_cham_algorithmic_bytes(self.handle, B, n_groups, p_max, steps))

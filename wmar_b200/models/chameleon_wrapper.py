@@ -39,7 +39,7 @@ def _stand_in_tokenizer(prompt):
 
 class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
     def __init__(self, modelpath=None, *, state_dict=None, tokenizer_state_dict=None, model_cfg=None, vq_cfg=None,
-                 tokenize=None, bpe2img=None, device="cuda", max_batch=5, vqgan_precision="3xtf32", seed=0, rng="torch",
+                 tokenize=None, bpe2img=None, device="cuda", max_batch=8, vqgan_precision="3xtf32", seed=0, rng="torch",
                  guidance_text=3.0, guidance_image=1.2, image_tokens_per_image=1024):
         super().__init__()
         self._device = torch.device(device)
@@ -94,7 +94,7 @@ class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
         if self._eng is None:
             self._eng = ChameleonEngine(self._state, c["n_layers"], c["n_heads"], c["n_kv_heads"],
                                         image_tokens=(IMAGE_TOKEN_LO, IMAGE_TOKEN_HI),
-                                        max_seq=self.codes_size * self.codes_size + 96, max_batch=min(self.max_batch, 5),
+                                        max_seq=self.codes_size * self.codes_size + 96, max_batch=min(self.max_batch, 8),
                                         norm_eps=c["norm_eps"], rope_theta=c["rope_theta"],
                                         qk_norm=c.get("qk_normalization", True), device=self._device)
         else:
