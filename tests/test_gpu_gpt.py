@@ -12,7 +12,20 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("N,K,split", [(1536, 1536, 0), (4608, 1536, 0), (6144, 1536, 3), (1536, 6144, 12),
                                        (16384, 1536, 0), (64, 128, 1), (1024, 1280, 0), (3840, 1280, 2)])
-def test_skinny_gemm_fp32_faithful(N, K, split):
+@pytest.mark.parametrize("engine", ["mma_sync", "tcgen05"])
+def test_skinny_gemm_fp32_faithful(N, K, split, engine):
+    from wmar_b200 import _lib
+    import ctypes
+    hook = _lib.lib().wmar_debug_set_gemm_engine
+    hook.argtypes = [ctypes.c_int]
+    hook(0 if engine == "tcgen05" else 1)      # tcgen05 kernel where the shape tiles (N % 128, K % 32), else mma.sync
+    try:
+        _skinny_gemm_case(N, K, split)
+    finally:
+        hook(1)
+
+
+def _skinny_gemm_case(N, K, split):
     from wmar_b200 import _lib
     g = torch.Generator().manual_seed(N + K)
     x = torch.randn(16, K, generator=g).cuda()
@@ -49,10 +62,15 @@ def _noise(seed, steps, B, V):
     return torch.empty(steps, B, V).exponential_(1)
 
 
-@pytest.mark.parametrize("name", ["tiny", "narrow"])
-def test_gpt_engine_matches_reference_golden(name):
+@pytest.mark.parametrize("name,step_mode", [("tiny", "graph"), ("narrow", "graph"), ("narrow", "fused")])
+def test_gpt_engine_matches_reference_golden(name, step_mode):
+    """step_mode "fused" = the tcgen05 / TMA / cluster block kernels (gpt_fused.cuh; needs d % 128 == 0, so not "tiny")."""
     from oracle import gpt as ogpt
-    g, w, eng, (V, block, L, H, d, steps, B) = _engine(name)
+    os.environ["WMAR_STEP"] = step_mode
+    try:
+        g, w, eng, (V, block, L, H, d, steps, B) = _engine(name)
+    finally:
+        os.environ.pop("WMAR_STEP", None)
     wm = make_wm("taming")
     cond = torch.from_numpy(g[f"{name}/cond"]).long()
     # logits of every step vs the oracle fed with the engine's own tokens (numerics, tolerance 2e-4 abs on O(1) logits)
