@@ -271,6 +271,25 @@ int wmar_vqgan_decode(wmar_vqgan *v, const int64_t *d_codes, int64_t B, float *d
 int wmar_vqgan_encode(wmar_vqgan *v, const float *d_images, int64_t B, int64_t *d_codes, void *stream);
 double wmar_vqgan_flops(const wmar_vqgan *v, int decode);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Evaluation augmentations: the transforms applied between codes_to_images and images_to_codes in
+ * fill_batch_log (generate.py:142-163).  Images fp32 NCHW [B][3][H][W] in [0,1], out of place.  Replaces
+ * wmar/augmentations/valuemetric.py:76-137 and geometric.py:26-117 (torchvision.transforms.functional below them).
+ *   BRIGHTNESS       params {factor}                                  clamp(factor * x, 0, 1)
+ *   GAUSSIAN_NOISE   params {std}, d_aux = N(0,1) noise [B][3][H][W]   clamp(x + noise * std, 0, 1)
+ *   GAUSSIAN_BLUR    params {k}, d_aux = k x k normalised weights       reflect pad, depthwise correlation, clamp
+ *   HFLIP
+ *   AFFINE_NEAREST   params = inverse affine [2][3] (torchvision F.rotate / F.affine convention), output OH x OW
+ *   CROP_RESIZE      params {h2, w2}: bilinear resize of x[:, :, :h2, :w2] back to H x W
+ *   CROP_PAD         params {h2, w2}: x[:, :, :h2, :w2] zero padded back to H x W
+ * ---------------------------------------------------------------------------------------------------------- */
+enum wmar_aug_op {
+    WMAR_AUG_BRIGHTNESS = 0, WMAR_AUG_GAUSSIAN_NOISE = 1, WMAR_AUG_GAUSSIAN_BLUR = 2, WMAR_AUG_HFLIP = 3,
+    WMAR_AUG_AFFINE_NEAREST = 4, WMAR_AUG_CROP_RESIZE = 5, WMAR_AUG_CROP_PAD = 6
+};
+int wmar_augment(int op, const float *d_in, float *d_out, int64_t B, int64_t H, int64_t W, int64_t OH, int64_t OW,
+                 const float *params, int n_params, const float *d_aux, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

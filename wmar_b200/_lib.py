@@ -96,6 +96,8 @@ EXPORTS = {
     "wmar_cham_select": (ctypes.c_int, [ctypes.POINTER(WmParams), ctypes.POINTER(SampleParams), c_voidp, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                         c_voidp, ctypes.c_int64, ctypes.c_int64, c_voidp, c_voidp, c_voidp, c_voidp]),
+    "wmar_augment": (ctypes.c_int, [ctypes.c_int, c_voidp, c_voidp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                    ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_float), ctypes.c_int, c_voidp, c_voidp]),
     "wmar_vqgan_create": (ctypes.c_int, [ctypes.POINTER(VqganConfig), ctypes.POINTER(c_voidp), ctypes.c_int,
                                          ctypes.POINTER(c_voidp)]),
     "wmar_vqgan_destroy": (None, [c_voidp]),
