@@ -101,6 +101,21 @@ void tc_gemm_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 void tc_gemm_set_dbg(int bits) { g_tc_dbg = bits; }
 
 int tc_weight_map(const float *W, int N, int K, CUtensorMap *out) { return weight_map(W, N, K, out); }
+
+// NHWC fp32 activations [B][H][W][C] -> 4-D map (C innermost), box [1][bh][bw][32], 128-byte swizzle, zero fill outside
+int tc_nhwc_map(const float *base, int B, int H, int W, int C, int bw, int bh, CUtensorMap *out) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(WMAR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver%s%s");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(WMAR_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC) failed%s%s");
+    return WMAR_OK;
+}
 bool tc_available() { return encode_fn() != nullptr; }
 
 void tc_gemm_forget_maps() {

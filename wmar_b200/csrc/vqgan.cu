@@ -15,6 +15,8 @@
 //   AttnBlock = norm.g, norm.b, q.w, q.b, k.w, k.b, v.w, v.b, proj_out.w, proj_out.b
 #include <vector>
 
+#include "conv_tc.cuh"
+#include "gemm_tc.cuh"
 #include "vqgan_kernels.cuh"
 
 using namespace wmar;
@@ -30,6 +32,7 @@ struct Op {
     const float *w, *b;
     int Hs, Ws, Cin, Ho, Wo, Cout, Cout_pad, ks, stride, pad, up;
     int final_out;  // decoder conv_out: NCHW + clamp into the caller's image
+    float *wlo;     // tcgen05 path (conv_tc.cuh): w - trunc_tf32(w), same layout as w; null = mma.sync kernel
     // gn
     const float *gamma, *beta;
     int swish, H, W, C;
@@ -82,7 +85,7 @@ struct Builder {
         Op o{};
         o.kind = OP_CONV; o.src = src; o.dst = dst; o.res = res;
         o.w = cur.next(); o.b = cur.next();
-        o.Hs = H; o.Ws = W; o.Cin = round_up(C, 32);
+        o.Hs = H; o.Ws = W; o.Cin = round_up(C, 32); o.C = C;
         const int Hl = up ? H * 2 : H, Wl = up ? W * 2 : W;
         o.Ho = stride == 2 ? Hl / 2 : Hl;
         o.Wo = stride == 2 ? Wl / 2 : Wl;
@@ -244,7 +247,39 @@ int build_plans(wmar_vqgan *v, const void *const *tab, int n) {
     return WMAR_OK;
 }
 
+// 3x3 / stride 1 / pad 1 convs whose shapes tile into 128 pixels x 128 channels go to the tcgen05 kernel
+bool conv_tc_eligible(const Op &o) {
+    if (o.ks != 3 || o.stride != 1 || o.pad != 1 || o.up || o.final_out) return false;
+    if (o.C != o.Cin || o.Cout % 128 != 0 || o.Cout != o.Cout_pad) return false;   // no channel padding on either side
+    if (o.Ho != o.Hs || o.Wo != o.Ws || o.Ws < 8) return false;
+    if (o.Ws >= 128) return o.Ws % 128 == 0;
+    return 128 % o.Ws == 0 && o.Hs % (128 / o.Ws) == 0 && 128 / o.Ws <= 256;
+}
+
+int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SM_ALLOC));
+        configured = true;
+    }
+    ConvTcArgs a{};
+    a.bias = o.b; a.resid = o.res >= 0 ? v->buf[o.res] : nullptr; a.out = v->buf[o.dst];
+    a.H = o.Hs; a.W = o.Ws; a.Cin = o.Cin; a.Cout = o.Cout;
+    a.bw = o.Ws >= 128 ? 128 : o.Ws; a.bh = 128 / a.bw;
+    a.tiles_x = o.Ws / a.bw; a.tiles_y = o.Hs / a.bh;
+    CUtensorMap mA, mWh, mWl;
+    int rc;
+    if ((rc = tc_nhwc_map(v->buf[o.src], B, o.Hs, o.Ws, o.Cin, a.bw, a.bh, &mA))) return rc;
+    if ((rc = tc_weight_map(o.w, o.Cout_pad, 9 * o.Cin, &mWh))) return rc;
+    if ((rc = tc_weight_map(o.wlo, o.Cout_pad, 9 * o.Cin, &mWl))) return rc;
+    dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)(o.Cout / 128));
+    conv3x3_tc_kernel<<<grid, CT_THREADS, CT_SM_ALLOC, s>>>(mA, mWh, mWl, a);
+    WMAR_LAUNCH_CHECK();
+    return WMAR_OK;
+}
+
 int run_conv(const wmar_vqgan *v, const Op &o, int B, float *final_out, cudaStream_t s) {
+    if (o.wlo != nullptr) return run_conv_tc(v, o, B, s);
     ConvArgs a{};
     a.in = v->buf[o.src]; a.w = o.w; a.bias = o.b;
     a.resid = o.res >= 0 ? v->buf[o.res] : nullptr;
@@ -351,6 +386,20 @@ int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights
     WMAR_CUDA_CHECK(cudaMalloc(&v->gn_partial, sizeof(double2) * 64 * 32 * (size_t)cfg->max_batch));
     row_sumsq_kernel<<<(cfg->n_embed + 7) / 8, 256>>>(v->codebook, v->ee, cfg->n_embed, cfg->embed_dim);
     WMAR_LAUNCH_CHECK();
+    // tcgen05 path for the 3x3 convs that tile (WMAR_CONV=v0 keeps everything on the mma.sync kernel): precompute w_lo
+    {
+        const char *e = getenv("WMAR_CONV");
+        const bool want_tc = !(e && e[0] == 'v') && tc_available();
+        for (auto *ops : {&v->enc, &v->dec})
+            for (Op &o : *ops) {
+                o.wlo = nullptr;
+                if (!want_tc || o.kind != OP_CONV || !conv_tc_eligible(o)) continue;
+                const size_t nw = (size_t)o.Cout_pad * 9 * o.Cin;
+                WMAR_CUDA_CHECK(cudaMalloc(&o.wlo, sizeof(float) * nw));
+                conv_tc_wlo_kernel<<<1024, 256>>>(o.w, o.wlo, nw);
+                WMAR_LAUNCH_CHECK();
+            }
+    }
     const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -363,6 +412,8 @@ int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights
 void wmar_vqgan_destroy(wmar_vqgan *v) {
     if (!v) return;
     cudaDeviceSynchronize();
+    for (auto *ops : {&v->enc, &v->dec})
+        for (Op &o : *ops) cudaFree(o.wlo);
     for (int i = 0; i < 6; i++) cudaFree(v->buf[i]);
     cudaFree(v->dots); cudaFree(v->zz); cudaFree(v->ee); cudaFree(v->gn_partial);
     delete v;
