@@ -33,6 +33,7 @@ struct Op {
     int Hs, Ws, Cin, Ho, Wo, Cout, Cout_pad, ks, stride, pad, up;
     int final_out;  // decoder conv_out: NCHW + clamp into the caller's image
     float *wlo;     // tcgen05 path (conv_tc.cuh): w - trunc_tf32(w), same layout as w; null = mma.sync kernel
+    int tmp;        // up convs on the tcgen05 path: buffer that receives the materialised nearest x2 input
     // gn
     const float *gamma, *beta;
     int swish, H, W, C;
@@ -90,7 +91,7 @@ struct Builder {
         o.Ho = stride == 2 ? Hl / 2 : Hl;
         o.Wo = stride == 2 ? Wl / 2 : Wl;
         o.Cout = cout; o.Cout_pad = round_up(cout, 64);
-        o.ks = ks; o.stride = stride; o.pad = pad; o.up = up; o.final_out = final_out ? 1 : 0;
+        o.ks = ks; o.stride = stride; o.pad = pad; o.up = up; o.final_out = final_out ? 1 : 0; o.tmp = -1; o.wlo = nullptr;
         ops->push_back(o);
         flops += 2.0 * o.Ho * o.Wo * (double)cout * (double)(ks * ks) * (double)C;
         H = o.Ho; W = o.Wo; C = cout;
@@ -232,7 +233,8 @@ int build_plans(wmar_vqgan *v, const void *const *tab, int n) {
         }
         if (l != 0) {
             int t = b.free_buf({b.x});
-            b.conv(b.x, t, -1, b.C, 3, 1, 1, 1);  // nearest x2 folded into the conv's input indexing
+            b.conv(b.x, t, -1, b.C, 3, 1, 1, 1);  // nearest x2 folded into the conv's input indexing (mma.sync kernel)
+            b.ops->back().tmp = b.free_buf({b.x, t});   // ... or materialised there for the tcgen05 kernel
             b.x = t;
             res *= 2;
         }
@@ -249,11 +251,27 @@ int build_plans(wmar_vqgan *v, const void *const *tab, int n) {
 
 // 3x3 / stride 1 / pad 1 convs whose shapes tile into 128 pixels x 128 channels go to the tcgen05 kernel
 bool conv_tc_eligible(const Op &o) {
-    if (o.ks != 3 || o.stride != 1 || o.pad != 1 || o.up || o.final_out) return false;
+    if (o.ks != 3 || o.stride != 1 || o.pad != 1 || o.final_out) return false;
+    if (o.up && o.tmp < 0) return false;
     if (o.C != o.Cin || o.Cout % 128 != 0 || o.Cout != o.Cout_pad) return false;   // no channel padding on either side
-    if (o.Ho != o.Hs || o.Wo != o.Ws || o.Ws < 8) return false;
-    if (o.Ws >= 128) return o.Ws % 128 == 0;
-    return 128 % o.Ws == 0 && o.Hs % (128 / o.Ws) == 0 && 128 / o.Ws <= 256;
+    const int Hi = o.up ? 2 * o.Hs : o.Hs, Wi = o.up ? 2 * o.Ws : o.Ws;            // conv input = (upsampled) source
+    if (o.Ho != Hi || o.Wo != Wi || Wi < 8) return false;
+    if (Wi >= 128) return Wi % 128 == 0;
+    return 128 % Wi == 0 && Hi % (128 / Wi) == 0 && 128 / Wi <= 256;
+}
+
+// nearest x2 (taming model.py:39-54 Upsample: F.interpolate(scale_factor=2, mode="nearest")), NHWC, 16-byte vectors
+__global__ void upsample2x_nhwc_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int B, int H, int W, int C4) {
+    const size_t n = (size_t)B * 2 * H * 2 * W * C4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        size_t p = i / C4;
+        const int x = (int)(p % (2 * W));
+        p /= 2 * W;
+        const int y = (int)(p % (2 * H));
+        const int b = (int)(p / (2 * H));
+        out[i] = in[(((size_t)b * H + (y >> 1)) * W + (x >> 1)) * C4 + c];
+    }
 }
 
 int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
@@ -262,14 +280,23 @@ int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
         WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SM_ALLOC));
         configured = true;
     }
+    const float *src = v->buf[o.src];
+    if (o.up) {
+        const size_t n4 = (size_t)B * o.Ho * o.Wo * (o.Cin / 4);
+        size_t gx = (n4 + 255) / 256;
+        upsample2x_nhwc_kernel<<<(unsigned)(gx > 148 * 32 ? 148 * 32 : gx), 256, 0, s>>>(
+            reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(v->buf[o.tmp]), B, o.Hs, o.Ws, o.Cin / 4);
+        WMAR_LAUNCH_CHECK();
+        src = v->buf[o.tmp];
+    }
     ConvTcArgs a{};
     a.bias = o.b; a.resid = o.res >= 0 ? v->buf[o.res] : nullptr; a.out = v->buf[o.dst];
-    a.H = o.Hs; a.W = o.Ws; a.Cin = o.Cin; a.Cout = o.Cout;
-    a.bw = o.Ws >= 128 ? 128 : o.Ws; a.bh = 128 / a.bw;
-    a.tiles_x = o.Ws / a.bw; a.tiles_y = o.Hs / a.bh;
+    a.H = o.Ho; a.W = o.Wo; a.Cin = o.Cin; a.Cout = o.Cout;
+    a.bw = o.Wo >= 128 ? 128 : o.Wo; a.bh = 128 / a.bw;
+    a.tiles_x = o.Wo / a.bw; a.tiles_y = o.Ho / a.bh;
     CUtensorMap mA, mWh, mWl;
     int rc;
-    if ((rc = tc_nhwc_map(v->buf[o.src], B, o.Hs, o.Ws, o.Cin, a.bw, a.bh, &mA))) return rc;
+    if ((rc = tc_nhwc_map(src, B, o.Ho, o.Wo, o.Cin, a.bw, a.bh, &mA))) return rc;
     if ((rc = tc_weight_map(o.w, o.Cout_pad, 9 * o.Cin, &mWh))) return rc;
     if ((rc = tc_weight_map(o.wlo, o.Cout_pad, 9 * o.Cin, &mWl))) return rc;
     dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)(o.Cout / 128));
