@@ -81,7 +81,7 @@ def detect():
     pk = float(peaks().get("bf16_tflops_sustained", 1363.5)) / 2.0    # TF32 dense = half the bf16 rate
     return {"workload": "detect_only_taming_encode_256_B16", "images_per_s_per_gpu": B * n_batches / (ms * 1e-3),
             "ms_per_batch_of_16": ms / n_batches,
-            "roofline": {"bound": "tensor", "kernel": "VQGAN encoder conv stack + codebook arg-min (3xTF32 mma.sync)",
+            "roofline": {"bound": "tensor", "kernel": "VQGAN encoder conv stack (tcgen05 3xTF32 implicit GEMM) + codebook arg-min",
                          "achieved": fl / ms / 1e9, "peak": pk, "unit": "TFLOP/s (useful fp32-equivalent)", "frac": fl / ms / 1e9 / pk},
             "detector": {"p_mean": float(torch.cat([s["pvalue"] for s in sts]).mean())}}
 
