@@ -46,17 +46,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
         ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t smem_desc_kmajor_sw128(uint32_t addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3fffu);
-    d |= (uint64_t)1 << 16;                    // LBO (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;          // SBO
-    d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-    return d;
-}
-
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapWh,
                   const __grid_constant__ CUtensorMap mapWl, const ConvTcArgs a) {
@@ -125,7 +114,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const uint32_t wb = smem_base + s * CT_STAGE_BYTES + CT_TILE_BYTES;   // [w_hi (128 rows) ; w_lo (128 rows)]
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
-                    const uint64_t bd = smem_desc_kmajor_sw128(wb + ks * 32);
+                    const uint64_t bd = tc05::smem_desc_kmajor_sw128(wb + ks * 32);
                     mma_tf32_ts(tmem, a_hi + ks * 8, bd, ID256, (c | ks) != 0 ? 1u : 0u);   // hi.hi | hi.lo
                     mma_tf32_ts(tmem + 128, a_lo + ks * 8, bd, ID128, 1u);                  // + lo.hi
                 }
