@@ -21,8 +21,23 @@ static bool v0_pdl() {
     return on == 1;
 }
 
+// probe only: WMAR_GEMM_TRACE=<pro><epi> (e.g. 11 = fc1) records globaltimer stamps of that kernel type
+__device__ unsigned long long g_gemm_trace_buf[16];   // a device global: nothing may be allocated under stream capture
+static unsigned long long *g_gemm_trace = nullptr;
+static int g_gemm_trace_kind = -1;
+static unsigned long long *gemm_trace_for(int pro, int epi) {
+    if (g_gemm_trace_kind == -1) {
+        const char *e = getenv("WMAR_GEMM_TRACE");
+        g_gemm_trace_kind = e ? atoi(e) : -2;
+        if (g_gemm_trace_kind >= 0) cudaGetSymbolAddress(reinterpret_cast<void **>(&g_gemm_trace), g_gemm_trace_buf);
+    }
+    return (g_gemm_trace_kind == pro * 10 + epi) ? g_gemm_trace : nullptr;
+}
+
 template <int PRO, int EPI>
-static int launch_t(const GemmArgs &a, cudaStream_t stream) {
+static int launch_t(const GemmArgs &a_in, cudaStream_t stream) {
+    GemmArgs a = a_in;
+    a.trace = gemm_trace_for(PRO, EPI);
     static bool configured = false;
     if (!configured) {
         WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -96,6 +111,13 @@ size_t g_ws_bytes = 0, g_counter_n = 0;
 static int g_probe_mode = 0;
 /* test/probe hook (not part of the product path): 0 = 3xTF32, 1 = 1xTF32, 2 = load-only */
 extern "C" void wmar_debug_set_gemm_mode(int mode) { g_probe_mode = mode; }
+/* probe only: copies the 16 stamps of the traced GEMM kind (WMAR_GEMM_TRACE) */
+extern "C" int wmar_debug_gemm_trace(unsigned long long *out) {
+    if (wmar::g_gemm_trace == nullptr) return -1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, wmar::g_gemm_trace, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost);
+    return 0;
+}
 /* test hook: 0 = tcgen05 kernel where eligible, 1 = mma.sync kernel everywhere */
 extern "C" void wmar_debug_set_gemm_engine(int engine) { wmar::g_gemm_engine = engine ? 1 : 0; }
 namespace wmar { void tc_gemm_set_pdl(int on); void tc_gemm_set_dbg(int bits); }

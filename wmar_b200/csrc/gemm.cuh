@@ -54,7 +54,9 @@ struct GemmArgs {
     float2 *stats_out;            // [N/64][16] or null
     float *ws;                    // [N/64][splits][16*64]
     unsigned *counters;           // [N/64], zero-initialised, self-resetting
+    unsigned long long *trace;    // probe only: [16] globaltimer stamps of CTA (0,0) / of the last arriver of tile 0
 };
+#define GM_TRACE(e) do { if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && (blockIdx.y == 0 || (e) >= 8)) { unsigned long long v_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v_)); a.trace[e] = v_; } } while (0)
 
 __device__ __forceinline__ float4 ldg_stream(const float *p) {
     float4 r;
@@ -99,26 +101,36 @@ __device__ __forceinline__ void chan_combine(float &n, float &mean, float &m2, f
 }
 
 // Per-row (mean, rstd) of X from the producer's tile partials; result in smem row_stats[16] (x = mean, y = rstd).
+// ONE warp per CTA does it: lane = (row, tile parity), every load of the lane in flight at once.  All CTAs of the grid
+// read the same few cache lines (n_tiles x 128 B) at the same moment right after the dependency resolves; with every
+// warp of every CTA loading them the L2 slices that own those lines serialised ~2000 requests per line (measured:
+// 4.4 us from griddepcontrol.wait to the statistics, profiles/r01_final_summary.md) -- one warp per CTA is 8x fewer.
 __device__ __forceinline__ void combine_row_stats(const float2 *__restrict__ stats_in, int n_tiles, int K, float eps,
                                                   float2 *row_stats) {
-    const int tid = threadIdx.x;
-    const int r = tid >> 4, sub = tid & 15;  // 16 threads per row, contiguous lanes
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x, r = lane & 15, half = lane >> 4;
+    constexpr int MAXT = 12;                      // tiles per lane held in registers (n_tiles <= 24 in one pass)
     float n = 0.f, mean = 0.f, m2 = 0.f;
     const float w = (float)(K / n_tiles);
-    for (int tl = sub; tl < n_tiles; tl += 16) {
-        float2 s = __ldcg(stats_in + tl * 16 + r);   // not hoistable above griddepcontrol.wait
-        chan_combine(n, mean, m2, w, s.x, s.y);
-    }
+    for (int t0 = 0; t0 < n_tiles; t0 += 2 * MAXT) {
+        float2 sv[MAXT];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        float nb = __shfl_xor_sync(0xffffffffu, n, o);
-        float mb = __shfl_xor_sync(0xffffffffu, mean, o);
-        float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
-        // fixed combination tree: lower lane index is always the left operand
-        if ((sub & o) == 0) chan_combine(n, mean, m2, nb, mb, m2b);
-        else { float tn = nb, tm = mb, t2 = m2b; chan_combine(tn, tm, t2, n, mean, m2); n = tn; mean = tm; m2 = t2; }
+        for (int k = 0; k < MAXT; k++) {
+            const int tl = t0 + half + 2 * k;
+            sv[k] = tl < n_tiles ? __ldcg(stats_in + tl * 16 + r) : make_float2(0.f, 0.f);   // not hoistable above the wait
+        }
+#pragma unroll
+        for (int k = 0; k < MAXT; k++)
+            if (t0 + half + 2 * k < n_tiles) chan_combine(n, mean, m2, w, sv[k].x, sv[k].y);
     }
-    if (sub == 0) row_stats[r] = make_float2(mean, 1.0f / sqrtf(m2 / (float)K + eps));
+    // even tiles (lanes 0-15) and odd tiles (lanes 16-31) of the same row: lower lane is the left operand
+    const float nb = __shfl_xor_sync(0xffffffffu, n, 16);
+    const float mb = __shfl_xor_sync(0xffffffffu, mean, 16);
+    const float m2b = __shfl_xor_sync(0xffffffffu, m2, 16);
+    if (half == 0) {
+        chan_combine(n, mean, m2, nb, mb, m2b);
+        row_stats[r] = make_float2(mean, 1.0f / sqrtf(m2 / (float)K + eps));
+    }
 }
 
 template <int PRO, int EPI, int MODE = 0>
@@ -155,8 +167,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
     for (int s0 = 0; s0 < GEMM_STAGES; s0++) issue(s0);
     // programmatic dependent launch: the next kernel of the step may start (and issue ITS first weight loads) while this
     // one runs; everything below reads what the previous kernel produced
+    GM_TRACE(0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    GM_TRACE(1);
 
     float2 st_g = make_float2(0.f, 1.f), st_g8 = make_float2(0.f, 1.f);
     if (PRO != PRO_NONE) {
@@ -166,6 +180,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
         st_g8 = row_stats[g + 8];
     }
 
+    GM_TRACE(2);
     float acc[GEMM_TILES][4];
 #pragma unroll
     for (int j = 0; j < GEMM_TILES; j++)
@@ -223,6 +238,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
             for (int j = 0; j < GEMM_TILES; j++) wcur[j] = *reinterpret_cast<const float4 *>(src + j * 512);
         }
         issue(it + GEMM_STAGES);
+        if (it < 4) GM_TRACE(3 + it);
 #pragma unroll
         for (int j = 0; j < GEMM_TILES; j++) {
             const float wv[4] = {wcur[j].x, wcur[j].y, wcur[j].z, wcur[j].w};
@@ -242,6 +258,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
             }
         }
     }
+    GM_TRACE(7);
     gm_cp_wait<0>();
     __syncthreads();   // every warp is done with its ring: the reduction buffer below aliases it
 
@@ -273,15 +290,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
             if (s_is_last) a.counters[tile] = 0u;
         }
         __syncthreads();
+        GM_TRACE(8 + (s_is_last ? 1 : 0));
         if (!s_is_last) return;
         __threadfence();
         v = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < a.splits; s++) {
-            float4 p = __ldcg(reinterpret_cast<const float4 *>(wst + (size_t)s * (GEMM_M * GEMM_NT) + m * GEMM_NT + nn));
-            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        for (int s0 = 0; s0 < a.splits; s0 += 4) {     // four partials in flight, summed in split order
+            float4 p[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                p[k] = s0 + k < a.splits ? __ldcg(reinterpret_cast<const float4 *>(wst + (size_t)(s0 + k) * (GEMM_M * GEMM_NT) + m * GEMM_NT + nn))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (s0 + k < a.splits) { v.x += p[k].x; v.y += p[k].y; v.z += p[k].z; v.w += p[k].w; }
         }
     }
 
+    GM_TRACE(10);
     // ---- epilogue ----
     const int n = n0 + nn;
     if (a.bias != nullptr) {
@@ -312,6 +337,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
         for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         if ((tid & 15) == 0) a.stats_out[tile * GEMM_M + m] = make_float2(mean, q);
     }
+    GM_TRACE(11);
 }
 
 // host-side launcher (graph-capturable)
