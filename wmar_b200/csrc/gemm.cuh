@@ -119,9 +119,17 @@ __device__ __forceinline__ void combine_row_stats(const float2 *__restrict__ sta
             const int tl = t0 + half + 2 * k;
             sv[k] = tl < n_tiles ? __ldcg(stats_in + tl * 16 + r) : make_float2(0.f, 0.f);   // not hoistable above the wait
         }
+        // equal-sized tiles: mean of the tile means, then M2 = sum M2_i + w * sum (mean_i - mean)^2 (no divisions)
+        float ms = 0.f, cnt = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXT; k++)
-            if (t0 + half + 2 * k < n_tiles) chan_combine(n, mean, m2, w, sv[k].x, sv[k].y);
+            if (t0 + half + 2 * k < n_tiles) { ms += sv[k].x; cnt += 1.f; }
+        const float mloc = cnt > 0.f ? ms / cnt : 0.f;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXT; k++)
+            if (t0 + half + 2 * k < n_tiles) { const float dd = sv[k].x - mloc; q += sv[k].y + w * dd * dd; }
+        chan_combine(n, mean, m2, cnt * w, mloc, q);
     }
     // even tiles (lanes 0-15) and odd tiles (lanes 16-31) of the same row: lower lane is the left operand
     const float nb = __shfl_xor_sync(0xffffffffu, n, 16);
