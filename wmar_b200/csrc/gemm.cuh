@@ -250,9 +250,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
 #pragma unroll
         for (int j = 0; j < GEMM_TILES; j++) {
             const float wv[4] = {wcur[j].x, wcur[j].y, wcur[j].z, wcur[j].w};
+            // weights: hi = trunc_tf32(w) (one LOP; the tensor core ignores the low 13 bits anyway), lo = w - hi exactly
+            // (fed as raw fp32 bits, truncated to TF32 by the MMA: residual <= 2^-21 |w|)
             uint32_t wh[4], wl[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) split_tf32(wv[e], wh[e], wl[e]);
+            for (int e = 0; e < 4; e++) {
+                wh[e] = __float_as_uint(wv[e]) & 0xffffe000u;
+                wl[e] = __float_as_uint(wv[e] - __uint_as_float(wh[e]));
+            }
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 const int e = 2 * half;
