@@ -91,7 +91,8 @@ int pick_splits(int N, int K, int n_sms) {
 }
 
 size_t gemm_ws_floats(int N, int K, int splits_v0, int n_sms) {
-    size_t v0 = (size_t)(N / GEMM_NT) * (size_t)splits_v0 * GEMM_M * GEMM_NT;
+    // x2: the flag-carrying hand-off stores {value, flag} pairs
+    size_t v0 = 2 * (size_t)(N / GEMM_NT) * (size_t)splits_v0 * GEMM_M * GEMM_NT;
     size_t tc = 0;
     if (N % TC_TILE_N == 0 && K % TC_KC == 0)
         tc = (size_t)(N / TC_TILE_N) * (size_t)tc_pick_splits(N, K, n_sms) * GEMM_M * TC_TILE_N;
@@ -150,6 +151,18 @@ extern "C" int wmar_skinny_gemm(const float *d_x, const float *d_w, const float 
     a.Y = d_y; a.ldy = (int)N;
     a.N = (int)N; a.K = (int)K; a.splits = splits;
     a.ws = g_ws; a.counters = g_counters;
+    {   // flags of the stand-alone entry: a host counter that never repeats within the workspace's lifetime
+        static unsigned call = 0;
+        static size_t ws_seen = 0;
+        if (ws_seen != g_ws_bytes || call >= (1u << 21)) {
+            WMAR_CUDA_CHECK(cudaMemsetAsync(g_ws, 0, g_ws_bytes, as_stream(stream)));
+            ws_seen = g_ws_bytes; call = 0;
+        }
+        a.ll_epoch = nullptr;
+        a.ll_epoch_val = call / 1023u;
+        a.ll_salt = 1u + (call % 1023u);
+        call++;
+    }
     if (g_probe_mode != 0) {
         dim3 grid((unsigned)(a.N / GEMM_NT), (unsigned)a.splits);
         WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO_NONE, EPI_STORE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));

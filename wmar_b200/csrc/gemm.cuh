@@ -54,6 +54,13 @@ struct GemmArgs {
     float2 *stats_out;            // [N/64][16] or null
     float *ws;                    // [N/64][splits][16*64]
     unsigned *counters;           // [N/64], zero-initialised, self-resetting
+    // flag-carrying split-K hand-off (ll_salt != 0): every 8-byte word of a partial is {value, flag}, written with
+    // one 64-bit store (single-copy atomic), so the partial needs no fence and no counter: the CTA of the LAST split
+    // (dispatched after the others) polls the words of the other splits until they carry this launch's flag and sums
+    // them in split order.  flag = (*ll_epoch + 1) * 1024 + ll_salt must be unique among all launches that have written
+    // into ws since it was last cleared (the engines use their token-step counter and the launch index within the step,
+    // and clear ws at the start of every generation).  ll_salt == 0: counter-based hand-off (fence + atomic).
+    const int *ll_epoch; unsigned ll_epoch_val; unsigned ll_salt;   // epoch = *ll_epoch, or ll_epoch_val when the pointer is null
     unsigned long long *trace;    // probe only: [16] globaltimer stamps of CTA (0,0) / of the last arriver of tile 0
 };
 #define GM_TRACE(e) do { if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && (blockIdx.y == 0 || (e) >= 8)) { unsigned long long v_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v_)); a.trace[e] = v_; } } while (0)
@@ -86,6 +93,16 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ unsigned long long ll_pack(float v, unsigned flag) {
+    return (unsigned long long)__float_as_uint(v) | ((unsigned long long)flag << 32);
+}
+__device__ __forceinline__ void ll_store2(unsigned long long *p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ll_load2(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -179,6 +196,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     GM_TRACE(1);
+    // this launch's hand-off flag (the load is consumed only after the main loop)
+    unsigned ll_flag = 0;
+    if (a.ll_salt != 0) ll_flag = ((unsigned)(a.ll_epoch != nullptr ? (unsigned)__ldcg(a.ll_epoch) : a.ll_epoch_val) + 1u) * 1024u + a.ll_salt;
 
     float2 st_g = make_float2(0.f, 1.f), st_g8 = make_float2(0.f, 1.f);
     if (PRO != PRO_NONE) {
@@ -291,8 +311,50 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
         v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
     }
 
-    // ---- split-K: last CTA of the tile reduces the partials in split order ----
-    if (a.splits > 1) {
+    // ---- split-K, flag-carrying hand-off: the CTA of the last split sums the partials in split order ----
+    if (a.splits > 1 && a.ll_salt != 0) {
+        unsigned long long *wst = reinterpret_cast<unsigned long long *>(a.ws) + ((size_t)tile * a.splits) * (GEMM_M * GEMM_NT) + m * GEMM_NT + nn;
+        if (split != a.splits - 1) {
+            unsigned long long *dst = wst + (size_t)split * (GEMM_M * GEMM_NT);
+            ll_store2(dst, ll_pack(v.x, ll_flag), ll_pack(v.y, ll_flag));
+            ll_store2(dst + 2, ll_pack(v.z, ll_flag), ll_pack(v.w, ll_flag));
+            GM_TRACE(8);
+            return;
+        }
+        GM_TRACE(9);
+        const float4 own = v;
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int others = a.splits - 1;
+        for (int s0 = 0; s0 < others; s0 += 4) {       // four partials in flight
+            unsigned long long q[4][4];
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (s0 + k < others) {
+                        const unsigned long long *src = wst + (size_t)(s0 + k) * (GEMM_M * GEMM_NT);
+                        ll_load2(src, q[k][0], q[k][1]);
+                        ll_load2(src + 2, q[k][2], q[k][3]);
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (s0 + k < others) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) ok = ok && ((unsigned)(q[k][c] >> 32) == ll_flag);
+                    }
+            } while (!ok);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (s0 + k < others) {
+                    v.x += __uint_as_float((unsigned)q[k][0]); v.y += __uint_as_float((unsigned)q[k][1]);
+                    v.z += __uint_as_float((unsigned)q[k][2]); v.w += __uint_as_float((unsigned)q[k][3]);
+                }
+        }
+        v.x += own.x; v.y += own.y; v.z += own.z; v.w += own.w;
+    }
+    // ---- split-K, counter hand-off: last CTA of the tile to arrive reduces the partials in split order ----
+    if (a.splits > 1 && a.ll_salt == 0) {
         float *wst = a.ws + ((size_t)tile * a.splits) * (GEMM_M * GEMM_NT);
         __stcg(reinterpret_cast<float4 *>(wst + (size_t)split * (GEMM_M * GEMM_NT) + m * GEMM_NT + nn), v);
         __threadfence();

@@ -54,6 +54,7 @@ struct wmar_gpt {
     std::vector<Layer> layers;
     // device scratch
     float *x, *qkv, *y, *hbuf, *logits, *kcache, *vcache, *ws;
+    size_t ws_bytes;
     float2 *stats;
     unsigned *counters;
     int64_t *seq;      // [16][block_size + 1]: conditioning token then the generated ids
@@ -386,6 +387,11 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
             launches += 4;
         }
     }
+    // flag-carrying split-K hand-off (gemm.cuh): epoch = the token-step counter, salt = launch index within the step;
+    // WMAR_LL=0 falls back to the counter hand-off (A/B runs)
+    static const bool ll_on = []() { const char *e = getenv("WMAR_LL"); return !(e && e[0] == '0'); }();
+    unsigned salt = 0;
+    auto ll = [&](GemmArgs &q) { if (ll_on) { q.ll_epoch = g->step; q.ll_salt = ++salt; } };
     for (int l = 0; l < (g->fused ? 0 : c.n_layer); l++) {
         const Layer &L = g->layers[l];
         GemmArgs a{};
@@ -393,6 +399,7 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
         // qkv = LN1(x) Wqkv^T + b
         a.X = g->x; a.ldx = d; a.W = L.wqkv; a.bias = L.bqkv; a.Y = g->qkv; a.ldy = 3 * d; a.N = 3 * d; a.K = d;
         a.splits = g->splits_qkv; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b; a.stats_in = g->stats; a.n_stat_tiles = stat_tiles;
+        ll(a);
         if ((rc = launch_skinny_gemm(PRO_LN, EPI_STORE, a, s))) return rc;
         {
             cudaLaunchConfig_t cfg{};
@@ -413,18 +420,21 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
         p.ws = g->ws; p.counters = g->counters;
         p.X = g->y; p.ldx = d; p.W = L.wproj; p.bias = L.bproj; p.Y = g->x; p.ldy = d; p.N = d; p.K = d;
         p.splits = g->splits_proj; p.resid = g->x; p.ld_resid = d; p.stats_out = g->stats;
+        ll(p);
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_RESID, p, s))) return rc;
         // m = GELU(LN2(x) W1^T + b1)
         GemmArgs f{};
         f.ws = g->ws; f.counters = g->counters; f.eps = 1e-5f;
         f.X = g->x; f.ldx = d; f.W = L.w1; f.bias = L.b1; f.Y = g->hbuf; f.ldy = 4 * d; f.N = 4 * d; f.K = d;
         f.splits = g->splits_fc1; f.ln_g = L.ln2_g; f.ln_b = L.ln2_b; f.stats_in = g->stats; f.n_stat_tiles = stat_tiles;
+        ll(f);
         if ((rc = launch_skinny_gemm(PRO_LN, EPI_GELU, f, s))) return rc;
         // x += m W2^T + b2
         GemmArgs o{};
         o.ws = g->ws; o.counters = g->counters;
         o.X = g->hbuf; o.ldx = 4 * d; o.W = L.w2; o.bias = L.b2; o.Y = g->x; o.ldy = d; o.N = d; o.K = 4 * d;
         o.splits = g->splits_fc2; o.resid = g->x; o.ld_resid = d; o.stats_out = g->stats;
+        ll(o);
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_RESID, o, s))) return rc;
         launches += 5;
     }
@@ -433,6 +443,7 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
     hd.X = g->x; hd.ldx = d; hd.W = g->head; hd.bias = nullptr; hd.Y = g->logits; hd.ldy = V; hd.N = V; hd.K = d;
     hd.splits = g->splits_head; hd.ln_g = g->lnf_g; hd.ln_b = g->lnf_b; hd.stats_in = g->stats;
     hd.n_stat_tiles = g->fused ? d / 32 : stat_tiles;
+    ll(hd);
     if ((rc = launch_skinny_gemm(PRO_LN, EPI_STORE, hd, s))) return rc;
     launches += 1;
     int *err = device_err_flag();
@@ -498,6 +509,7 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
     WMAR_CUDA_CHECK(cudaMalloc(&g->kcache, sizeof(float) * kv_elems));
     WMAR_CUDA_CHECK(cudaMalloc(&g->vcache, sizeof(float) * kv_elems));
     WMAR_CUDA_CHECK(cudaMalloc(&g->ws, sizeof(float) * (ws_floats ? ws_floats : 1)));
+    g->ws_bytes = sizeof(float) * (ws_floats ? ws_floats : 1);
     WMAR_CUDA_CHECK(cudaMalloc(&g->stats, sizeof(float2) * (d / 32) * 16));
     WMAR_CUDA_CHECK(cudaMalloc(&g->counters, sizeof(unsigned) * max_tiles));
     WMAR_CUDA_CHECK(cudaMalloc(&g->seq, sizeof(int64_t) * 16 * (cfg->block_size + 1)));
@@ -539,6 +551,7 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
             if (ws_floats < P * 16 * d) {
                 cudaFree(g->ws);
                 WMAR_CUDA_CHECK(cudaMalloc(&g->ws, sizeof(float) * P * 16 * d));
+                g->ws_bytes = sizeof(float) * P * 16 * d;
             }
             WMAR_CUDA_CHECK(cudaMalloc(&g->ws2, sizeof(float) * P * 16 * d));
             WMAR_CUDA_CHECK(cudaMalloc(&g->hpart, sizeof(float) * (size_t)(4 * d / 128) * FB_MLP_CS * 16 * 128));
@@ -605,6 +618,8 @@ int wmar_gpt_sample(wmar_gpt *g, const wmar_wm_params *wm, const wmar_sample_par
         g->graph_smem = smem;
         g->graph_B = (int)B;
     }
+    // the step counter restarts at 0: stale {value, flag} words of the previous generation must not match
+    if (!g->fused) WMAR_CUDA_CHECK(cudaMemsetAsync(g->ws, 0, g->ws_bytes, s));
     if (g->fused)
         WMAR_CUDA_CHECK(cudaMemsetAsync(g->hflag, 0, sizeof(unsigned) * (size_t)g->cfg.n_layer * (4 * g->cfg.n_embd / 128), s));
     init_call_kernel<<<1, 32, 0, s>>>(g->d_call, g->seq, g->cfg.block_size + 1, g->step);
