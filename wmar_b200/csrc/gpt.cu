@@ -154,6 +154,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const float *q
         k4a[u] = j < t ? *reinterpret_cast<const float4 *>(K + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
         v4a[u] = j < t ? *reinterpret_cast<const float4 *>(Vc + (size_t)j * HD + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // keys past the register batch: ask L2 for their lines now, so that the in-loop loads after the wait are L2 hits
+    if (t > GROUPS * BATCH) {
+        const size_t bytes = (size_t)(t - GROUPS * BATCH) * HD * sizeof(float);
+        const char *kp = reinterpret_cast<const char *>(K + (size_t)GROUPS * BATCH * HD);
+        const char *vp = reinterpret_cast<const char *>(Vc + (size_t)GROUPS * BATCH * HD);
+        for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)ATT_THREADS * 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + off));
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");   // qkv comes from the previous kernel
     const float4 q4 = __ldcg(reinterpret_cast<const float4 *>(q + 4 * sub));
     const float4 kn4 = __ldcg(reinterpret_cast<const float4 *>(kn + 4 * sub)), vn4 = __ldcg(reinterpret_cast<const float4 *>(vn + 4 * sub));

@@ -70,6 +70,7 @@ struct wmar_rar {
     // the adaLN modulation GEMMs depend only on the conditioning, not on x: they run on a forked branch of the step
     // graph, off the critical path, with their own split-K workspace; mod holds one [16][6d] block per layer
     float *ws_side;
+    size_t ws_bytes, ws_side_bytes;
     unsigned *counters_side;
     int launches_per_pass;
 };
@@ -325,12 +326,18 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
         WMAR_CUDA_CHECK(cudaEventRecord(g_fork_event(), s));
         WMAR_CUDA_CHECK(cudaStreamWaitEvent(side, g_fork_event(), 0));
     }
+    // flag-carrying split-K hand-off (gemm.cuh): epoch = the pass counter, salt = launch index within the pass
+    static const bool ll_on = []() { const char *e = getenv("WMAR_LL"); return !(e && e[0] == '0'); }();
+    WMAR_REQUIRE(5 * c.n_layer + 2 < 1024, "too many GEMM launches per pass for the hand-off flag");
+    unsigned salt = 0;
+    auto ll = [&](GemmArgs &q) { if (ll_on) { q.ll_epoch = g->pos; q.ll_salt = ++salt; } };
     for (int l = 0; l < c.n_layer; l++) {
         const RarLayer &L = g->layers[l];
         GemmArgs m{};
         m.ws = g->ws_side; m.counters = g->counters_side;
         m.X = g->csilu; m.ldx = d; m.W = L.wada; m.bias = L.bada; m.Y = g->mod + l * mod_ld; m.ldy = 6 * d; m.N = 6 * d; m.K = d;
         m.splits = g->s_ada;
+        ll(m);
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_STORE, m, ms))) return rc;
         if (capturing) WMAR_CUDA_CHECK(cudaEventRecord(g_layer_event(l), side));
     }
@@ -339,6 +346,7 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
         hm.ws = g->ws_side; hm.counters = g->counters_side;
         hm.X = g->csilu; hm.ldx = d; hm.W = g->whada; hm.bias = g->bhada; hm.Y = g->hmod; hm.ldy = 2 * d; hm.N = 2 * d; hm.K = d;
         hm.splits = g->s_hada;
+        ll(hm);
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_STORE, hm, ms))) return rc;
         if (capturing) WMAR_CUDA_CHECK(cudaEventRecord(g_layer_event(c.n_layer), side));
     }
@@ -351,6 +359,7 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
         a.X = g->x; a.ldx = d; a.W = L.wqkv; a.bias = L.bqkv; a.Y = g->qkv; a.ldy = 3 * d; a.N = 3 * d; a.K = d;
         a.splits = g->s_qkv; a.ln_g = L.n1_g; a.ln_b = L.n1_b; a.stats_in = g->stats; a.n_stat_tiles = stat_tiles;
         a.mod_shift = mod; a.mod_scale = mod + d; a.ld_mod = 6 * d;
+        ll(a);
         if ((rc = launch_skinny_gemm(PRO_ADALN, EPI_STORE, a, s))) return rc;
         rar_attn_kernel<<<dim3(H, 2 * B), RAR_ATT_THREADS, 0, s>>>(g->qkv, d, H, g->hd, g->T, L.qn_g, L.qn_b, L.kn_g, L.kn_b,
                                                                   g->kcache, g->vcache, l, g->pos, g->y);
@@ -360,18 +369,21 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
         p.X = g->y; p.ldx = d; p.W = L.wproj; p.bias = L.bproj; p.Y = g->x; p.ldy = d; p.N = d; p.K = d;
         p.splits = g->s_proj; p.resid = g->x; p.ld_resid = d; p.gate = mod + 2 * d; p.ld_gate = 6 * d;
         p.stats_out = g->stats;
+        ll(p);
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_GATE_RESID, p, s))) return rc;
         GemmArgs f{};
         f.ws = g->ws; f.counters = g->counters; f.eps = 1e-6f;
         f.X = g->x; f.ldx = d; f.W = L.w1; f.bias = L.b1; f.Y = g->hbuf; f.ldy = mlp; f.N = mlp; f.K = d;
         f.splits = g->s_fc1; f.ln_g = L.n2_g; f.ln_b = L.n2_b; f.stats_in = g->stats; f.n_stat_tiles = stat_tiles;
         f.mod_shift = mod + 3 * d; f.mod_scale = mod + 4 * d; f.ld_mod = 6 * d;
+        ll(f);
         if ((rc = launch_skinny_gemm(PRO_ADALN, EPI_GELU, f, s))) return rc;
         GemmArgs o{};
         o.ws = g->ws; o.counters = g->counters;
         o.X = g->hbuf; o.ldx = mlp; o.W = L.w2; o.bias = L.b2; o.Y = g->x; o.ldy = d; o.N = d; o.K = mlp;
         o.splits = g->s_fc2; o.resid = g->x; o.ld_resid = d; o.gate = mod + 5 * d; o.ld_gate = 6 * d;
         o.stats_out = g->stats;
+        ll(o);
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_GATE_RESID, o, s))) return rc;
         launches += 6;
     }
@@ -381,7 +393,8 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
     lm.X = g->x; lm.ldx = d; lm.W = g->wlm; lm.bias = g->blm; lm.Y = g->logits; lm.ldy = V; lm.N = V; lm.K = d;
     lm.splits = g->s_lm; lm.ln_g = nullptr; lm.ln_b = nullptr; lm.stats_in = g->stats; lm.n_stat_tiles = stat_tiles;
     lm.mod_scale = g->hmod; lm.mod_shift = g->hmod + d; lm.ld_mod = 2 * d;  // scale FIRST (rar.py:131)
-    if ((rc = launch_skinny_gemm(PRO_ADALN, EPI_STORE, lm, s))) return rc;
+    ll(lm);
+        if ((rc = launch_skinny_gemm(PRO_ADALN, EPI_STORE, lm, s))) return rc;
     int *err = device_err_flag();
     WMAR_REQUIRE(err != nullptr, "cannot allocate the device error flag");
     rar_guide_kernel<<<B, 256, 0, s>>>(g->d_call, g->logits, g->guided, V, g->pos);
@@ -450,6 +463,7 @@ int wmar_rar_create(const wmar_rar_config *cfg, const void *const *d_weights, in
     {
         const size_t side_ws = std::max(gemm_ws_floats(6 * d, d, g->s_ada, g->n_sms), gemm_ws_floats(2 * d, d, g->s_hada, g->n_sms));
         WMAR_CUDA_CHECK(cudaMalloc(&g->ws_side, sizeof(float) * (side_ws ? side_ws : 1)));
+        g->ws_side_bytes = sizeof(float) * (side_ws ? side_ws : 1);
         WMAR_CUDA_CHECK(cudaMalloc(&g->counters_side, sizeof(unsigned) * (6 * d / GEMM_NT)));
         WMAR_CUDA_CHECK(cudaMemset(g->counters_side, 0, sizeof(unsigned) * (6 * d / GEMM_NT)));
     }
@@ -462,6 +476,7 @@ int wmar_rar_create(const wmar_rar_config *cfg, const void *const *d_weights, in
     WMAR_CUDA_CHECK(cudaMalloc(&g->kcache, sizeof(float) * kv_elems));
     WMAR_CUDA_CHECK(cudaMalloc(&g->vcache, sizeof(float) * kv_elems));
     WMAR_CUDA_CHECK(cudaMalloc(&g->ws, sizeof(float) * ws_floats));
+    g->ws_bytes = sizeof(float) * ws_floats;
     WMAR_CUDA_CHECK(cudaMalloc(&g->stats, sizeof(float2) * (d / 64) * 16));
     WMAR_CUDA_CHECK(cudaMalloc(&g->counters, sizeof(unsigned) * max_tiles));
     WMAR_CUDA_CHECK(cudaMalloc(&g->ids, sizeof(int64_t) * 8 * cfg->image_seq_len));
@@ -544,6 +559,9 @@ int wmar_rar_sample(wmar_rar *g, const wmar_wm_params *wm, const wmar_sample_par
         g->graph_smem = smem;
         g->graph_B = (int)B;
     }
+    // the pass counter restarts at 0: stale {value, flag} words of the previous generation must not match
+    WMAR_CUDA_CHECK(cudaMemsetAsync(g->ws, 0, g->ws_bytes, s));
+    WMAR_CUDA_CHECK(cudaMemsetAsync(g->ws_side, 0, g->ws_side_bytes, s));
     rar_init_kernel<<<1, 1, 0, s>>>(g->pos);
     WMAR_LAUNCH_CHECK();
     for (int64_t i = 0; i <= steps; i++) {  // pass 0 = cls token (fills the cache only), pass i >= 1 samples token i-1
