@@ -69,6 +69,7 @@ struct wmar_cham {
     const float *norm_w;
     std::vector<ChamLayer> layers;
     float *x, *qkv, *y, *h13, *logits, *guided, *ws;
+    size_t ws_bytes;
     __nv_bfloat16 *kcache, *vcache;
     float2 *stats;
     unsigned *counters;
@@ -373,12 +374,18 @@ int cham_enqueue_pass(wmar_cham *g, int B, int n_groups, size_t sample_smem, cud
     cham_embed_kernel<<<16, 256, 0, s>>>(g->d_call, g->pass, g->seq, c.max_seq, g->tok_emb, d, V, g->x, g->stats, g->rowpos);
     WMAR_LAUNCH_CHECK();
     launches++;
+    // flag-carrying split-K hand-off (gemm.cuh): epoch = the pass counter, salt = launch index within the pass
+    static const bool ll_on = []() { const char *e = getenv("WMAR_LL"); return !(e && e[0] == '0'); }();
+    WMAR_REQUIRE(4 * c.n_layer + 1 < 1024, "too many GEMM launches per pass for the hand-off flag");
+    unsigned salt = 0;
+    auto ll = [&](Bf16GemmArgs &q) { if (ll_on) { q.ll_epoch = g->pass; q.ll_salt = ++salt; } };
     for (int l = 0; l < c.n_layer; l++) {
         const ChamLayer &L = g->layers[l];
         Bf16GemmArgs a{};
         a.ws = g->ws; a.counters = g->counters; a.eps = c.norm_eps;
         a.X = g->x; a.ldx = d; a.W = L.wqkv; a.Y = g->qkv; a.ldy = qkv_n; a.N = qkv_n; a.K = d; a.splits = g->s_qkv;
         a.rms_w = L.attn_norm; a.stats_in = g->stats; a.n_stat_tiles = stat_tiles;
+        ll(a);
         if ((rc = launch_skinny_gemm_bf16(BPRO_RMS, BEPI_STORE, a, s))) return rc;
         {
             cudaLaunchConfig_t cfg{};
@@ -399,6 +406,7 @@ int cham_enqueue_pass(wmar_cham *g, int B, int n_groups, size_t sample_smem, cud
         o.ws = g->ws; o.counters = g->counters;
         o.X = g->y; o.ldx = H * g->hd; o.W = L.wo; o.Y = g->x; o.ldy = d; o.N = d; o.K = H * g->hd; o.splits = g->s_wo;
         o.resid = g->x; o.ld_resid = d; o.stats_out = g->stats;
+        ll(o);
         if ((rc = launch_skinny_gemm_bf16(BPRO_NONE, BEPI_RESID, o, s))) return rc;
         Bf16GemmArgs f{};
         f.ws = g->ws; f.counters = g->counters; f.eps = c.norm_eps;
@@ -406,11 +414,13 @@ int cham_enqueue_pass(wmar_cham *g, int B, int n_groups, size_t sample_smem, cud
         // writes h = silu(x1) * x3 directly
         f.X = g->x; f.ldx = d; f.W = L.w13; f.Y = g->h13; f.ldy = F; f.N = 2 * F; f.K = d; f.splits = g->s_w13;
         f.rms_w = L.ffn_norm; f.stats_in = g->stats; f.n_stat_tiles = stat_tiles;
+        ll(f);
         if ((rc = launch_skinny_gemm_bf16(BPRO_RMS, BEPI_SWIGLU, f, s))) return rc;
         Bf16GemmArgs w{};
         w.ws = g->ws; w.counters = g->counters;
         w.X = g->h13; w.ldx = F; w.W = L.w2; w.Y = g->x; w.ldy = d; w.N = d; w.K = F; w.splits = g->s_w2;
         w.resid = g->x; w.ld_resid = d; w.stats_out = g->stats;
+        ll(w);
         if ((rc = launch_skinny_gemm_bf16(BPRO_NONE, BEPI_RESID, w, s))) return rc;
         launches += 5;
     }
@@ -418,7 +428,8 @@ int cham_enqueue_pass(wmar_cham *g, int B, int n_groups, size_t sample_smem, cud
     hd.ws = g->ws; hd.counters = g->counters; hd.eps = c.norm_eps;
     hd.X = g->x; hd.ldx = d; hd.W = g->wout; hd.Y = g->logits; hd.ldy = V; hd.N = V; hd.K = d; hd.splits = g->s_out;
     hd.rms_w = g->norm_w; hd.stats_in = g->stats; hd.n_stat_tiles = stat_tiles;
-    if ((rc = launch_skinny_gemm_bf16(BPRO_RMS, BEPI_STORE, hd, s))) return rc;
+    ll(hd);
+        if ((rc = launch_skinny_gemm_bf16(BPRO_RMS, BEPI_STORE, hd, s))) return rc;
     int *err = device_err_flag();
     WMAR_REQUIRE(err != nullptr, "cannot allocate the device error flag");
     cham_guide_kernel<<<B, 256, 0, s>>>(g->d_call, g->logits, V, c.image_token_lo, g->W, g->guided, g->pass);
@@ -478,7 +489,7 @@ int wmar_cham_create(const wmar_cham_config *cfg, const void *const *d_weights, 
     size_t ws_floats = 1;
     int max_tiles = 1;
     auto upd = [&](int N, int S) {
-        size_t n = (size_t)(N / GEMM_NT) * S * GEMM_M * GEMM_NT;
+        size_t n = 2 * (size_t)(N / GEMM_NT) * S * GEMM_M * GEMM_NT;   // x2: {value, flag} words of the split-K hand-off
         if (n > ws_floats) ws_floats = n;
         if (N / GEMM_NT > max_tiles) max_tiles = N / GEMM_NT;
     };
@@ -493,6 +504,7 @@ int wmar_cham_create(const wmar_cham_config *cfg, const void *const *d_weights, 
     WMAR_CUDA_CHECK(cudaMalloc(&g->kcache, sizeof(__nv_bfloat16) * kv_elems));
     WMAR_CUDA_CHECK(cudaMalloc(&g->vcache, sizeof(__nv_bfloat16) * kv_elems));
     WMAR_CUDA_CHECK(cudaMalloc(&g->ws, sizeof(float) * ws_floats));
+    g->ws_bytes = sizeof(float) * ws_floats;
     WMAR_CUDA_CHECK(cudaMalloc(&g->stats, sizeof(float2) * (d / 64) * 16));
     WMAR_CUDA_CHECK(cudaMalloc(&g->counters, sizeof(unsigned) * max_tiles));
     WMAR_CUDA_CHECK(cudaMalloc(&g->seq, sizeof(int64_t) * (size_t)cfg->max_batch * cfg->max_seq));
@@ -587,6 +599,8 @@ int wmar_cham_sample(wmar_cham *g, const wmar_wm_params *wm, const wmar_sample_p
         g->graph_smem = smem;
         g->graph_B = (int)B * 4 + n_groups;
     }
+    // the pass counter restarts at 0: stale {value, flag} words of the previous generation must not match
+    WMAR_CUDA_CHECK(cudaMemsetAsync(g->ws, 0, g->ws_bytes, s));
     cham_init_kernel<<<(unsigned)B, 64, 0, s>>>(g->d_call, g->seq, g->cfg.max_seq, g->pass);
     WMAR_LAUNCH_CHECK();
     const int64_t passes = p_max + steps - 1;

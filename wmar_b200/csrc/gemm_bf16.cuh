@@ -47,6 +47,10 @@ struct Bf16GemmArgs {
     float2 *stats_out;            // [N/64][16] or null
     float *ws;
     unsigned *counters;
+    // flag-carrying split-K hand-off, see GemmArgs in gemm.cuh (ws then holds 8-byte {value, flag} words).  In this
+    // persistent kernel the reducer is the CTA that owns the item of the LAST split; it only ever waits for items with
+    // a lower index, which are owned by other resident CTAs or lie behind it, so the wait cannot deadlock.
+    const int *ll_epoch; unsigned ll_salt;
 };
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -118,6 +122,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
     for (int s0 = 0; s0 < GEMM_STAGES; s0++) issue(blockIdx.x, s0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    unsigned ll_flag = 0;
+    if (a.ll_salt != 0) ll_flag = ((unsigned)__ldcg(a.ll_epoch) + 1u) * 1024u + a.ll_salt;
 
     float rs_g = 1.f, rs_g8 = 1.f;
     if (PRO == BPRO_RMS) {
@@ -221,7 +228,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
 #pragma unroll
     for (int s0 = 0; s0 < GEMM_STAGES; s0++) issue(item + (int)gridDim.x, s0);
 
-    if (a.splits > 1) {
+    if (a.splits > 1 && a.ll_salt != 0) {
+        unsigned long long *wst = reinterpret_cast<unsigned long long *>(a.ws) + ((size_t)tile * a.splits) * (GEMM_M * GEMM_NT) + m * GEMM_NT + nn;
+        if (split != a.splits - 1) {
+            unsigned long long *dst = wst + (size_t)split * (GEMM_M * GEMM_NT);
+            ll_store2(dst, ll_pack(v.x, ll_flag), ll_pack(v.y, ll_flag));
+            ll_store2(dst + 2, ll_pack(v.z, ll_flag), ll_pack(v.w, ll_flag));
+            continue;                   // CTA-uniform; `red` is protected by the barrier after the cross-warp reduction
+        }
+        const float4 own = v;
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int others = a.splits - 1;
+        for (int s0 = 0; s0 < others; s0 += 4) {
+            unsigned long long q[4][4];
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (s0 + k < others) {
+                        const unsigned long long *src = wst + (size_t)(s0 + k) * (GEMM_M * GEMM_NT);
+                        ll_load2(src, q[k][0], q[k][1]);
+                        ll_load2(src + 2, q[k][2], q[k][3]);
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (s0 + k < others) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) ok = ok && ((unsigned)(q[k][c] >> 32) == ll_flag);
+                    }
+            } while (!ok);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (s0 + k < others) {
+                    v.x += __uint_as_float((unsigned)q[k][0]); v.y += __uint_as_float((unsigned)q[k][1]);
+                    v.z += __uint_as_float((unsigned)q[k][2]); v.w += __uint_as_float((unsigned)q[k][3]);
+                }
+        }
+        v.x += own.x; v.y += own.y; v.z += own.z; v.w += own.w;
+    }
+    if (a.splits > 1 && a.ll_salt == 0) {
         float *wst = a.ws + ((size_t)tile * a.splits) * (GEMM_M * GEMM_NT);
         __stcg(reinterpret_cast<float4 *>(wst + (size_t)split * (GEMM_M * GEMM_NT) + m * GEMM_NT + nn), v);
         __threadfence();
