@@ -134,6 +134,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
         rs_g8 = row_rs[g + 8];
     }
 
+    float4 nxa0, nxa1, nxb0, nxb1, nw0, nw1;
+    nxa0 = nxa1 = nxb0 = nxb1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    nw0 = nw1 = make_float4(1.f, 1.f, 1.f, 1.f);
+    auto load_x = [&](int item, int it) {
+        if (item < n_items && it < iters) {
+            const int k = (item / tiles) * KS + warp * BG_KI + 8 * t + it * KSTEP;
+            const float *p0 = a.X + (size_t)g * a.ldx + k, *p1 = a.X + (size_t)(g + 8) * a.ldx + k;
+            nxa0 = __ldcg(reinterpret_cast<const float4 *>(p0)); nxa1 = __ldcg(reinterpret_cast<const float4 *>(p0 + 4));
+            nxb0 = __ldcg(reinterpret_cast<const float4 *>(p1)); nxb1 = __ldcg(reinterpret_cast<const float4 *>(p1 + 4));
+            if (PRO == BPRO_RMS) {
+                nw0 = __ldg(reinterpret_cast<const float4 *>(a.rms_w + k)); nw1 = __ldg(reinterpret_cast<const float4 *>(a.rms_w + k + 4));
+            }
+        }
+    };
+    load_x(blockIdx.x, 0);
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int tile = item % tiles, split = item / tiles;
     const int n0 = tile * GEMM_NT;
@@ -144,22 +159,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[j][c] = 0.f;
 
-    const float *x_g = a.X + (size_t)g * a.ldx + kw0 + 8 * t;
-    const float *x_g8 = a.X + (size_t)(g + 8) * a.ldx + kw0 + 8 * t;
-
     for (int it = 0; it < iters; it++) {
         const int koff = it * KSTEP;
+        // this iteration's activations (and RMSNorm weights) were requested one iteration ago; request the next ones --
+        // the next iteration's, or the first of this CTA's next item -- before touching them: an L2 round trip under
+        // the weight stream costs more than the iteration's math (knock-out: 19 % of the Anole-7B pass)
         float xs[2][8];
-        {
-            const float4 a0 = *reinterpret_cast<const float4 *>(x_g + koff), a1 = *reinterpret_cast<const float4 *>(x_g + koff + 4);
-            const float4 b0 = *reinterpret_cast<const float4 *>(x_g8 + koff), b1 = *reinterpret_cast<const float4 *>(x_g8 + koff + 4);
-            xs[0][0] = a0.x; xs[0][1] = a0.y; xs[0][2] = a0.z; xs[0][3] = a0.w; xs[0][4] = a1.x; xs[0][5] = a1.y; xs[0][6] = a1.z; xs[0][7] = a1.w;
-            xs[1][0] = b0.x; xs[1][1] = b0.y; xs[1][2] = b0.z; xs[1][3] = b0.w; xs[1][4] = b1.x; xs[1][5] = b1.y; xs[1][6] = b1.z; xs[1][7] = b1.w;
-        }
+        xs[0][0] = nxa0.x; xs[0][1] = nxa0.y; xs[0][2] = nxa0.z; xs[0][3] = nxa0.w; xs[0][4] = nxa1.x; xs[0][5] = nxa1.y; xs[0][6] = nxa1.z; xs[0][7] = nxa1.w;
+        xs[1][0] = nxb0.x; xs[1][1] = nxb0.y; xs[1][2] = nxb0.z; xs[1][3] = nxb0.w; xs[1][4] = nxb1.x; xs[1][5] = nxb1.y; xs[1][6] = nxb1.z; xs[1][7] = nxb1.w;
+        const float wv[8] = {nw0.x, nw0.y, nw0.z, nw0.w, nw1.x, nw1.y, nw1.z, nw1.w};
+        if (it + 1 < iters) load_x(item, it + 1);
+        else load_x(item + (int)gridDim.x, 0);
         if (PRO == BPRO_RMS) {
-            const int k = kw0 + 8 * t + koff;
-            const float4 w0 = *reinterpret_cast<const float4 *>(a.rms_w + k), w1 = *reinterpret_cast<const float4 *>(a.rms_w + k + 4);
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 // xformers rms_norm: (x * rsqrt(mean(x^2) + eps)) * weight in fp32, stored as bf16 (the pack below rounds)
@@ -168,6 +179,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
             }
         }
         if (PRO == BPRO_SWIGLU) {
+            const float *x_g = a.X + (size_t)g * a.ldx + kw0 + 8 * t;
+            const float *x_g8 = a.X + (size_t)(g + 8) * a.ldx + kw0 + 8 * t;
             const float4 c0 = *reinterpret_cast<const float4 *>(x_g + koff + a.swiglu_off), c1 = *reinterpret_cast<const float4 *>(x_g + koff + a.swiglu_off + 4);
             const float4 d0 = *reinterpret_cast<const float4 *>(x_g8 + koff + a.swiglu_off), d1 = *reinterpret_cast<const float4 *>(x_g8 + koff + a.swiglu_off + 4);
             const float x3[2][8] = {{c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w}};
@@ -192,18 +205,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_bf16_kernel(Bf16G
         }
         // this iteration's weights have landed; pull them into registers and hand the stage to iteration it + STAGES
         gm_cp_wait<GEMM_STAGES - 1>();
-        uint4 wcur[GEMM_TILES];
         {
             const uint8_t *src = gemm_smem + (warp * GEMM_STAGES + (it % GEMM_STAGES)) * GEMM_STAGE_BYTES + lane * 16;
 #pragma unroll
-            for (int j = 0; j < GEMM_TILES; j++) wcur[j] = *reinterpret_cast<const uint4 *>(src + j * 512);
+            for (int j = 0; j < GEMM_TILES; j++) {
+                const uint4 w = *reinterpret_cast<const uint4 *>(src + j * 512);
+                mma_bf16(acc[j], af[0][0], af[0][1], af[0][2], af[0][3], w.x, w.y);
+                mma_bf16(acc[j], af[1][0], af[1][1], af[1][2], af[1][3], w.z, w.w);
+            }
         }
-        issue(item, it + GEMM_STAGES);
-#pragma unroll
-        for (int j = 0; j < GEMM_TILES; j++) {
-            mma_bf16(acc[j], af[0][0], af[0][1], af[0][2], af[0][3], wcur[j].x, wcur[j].y);
-            mma_bf16(acc[j], af[1][0], af[1][1], af[1][2], af[1][3], wcur[j].z, wcur[j].w);
-        }
+        issue(item, it + GEMM_STAGES);   // after the reads above: the stage is this lane's own
     }
     gm_cp_wait<0>();
     __syncthreads();   // every warp is done with its ring: the reduction buffer below aliases it
