@@ -400,6 +400,7 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
     // flag-carrying split-K hand-off (gemm.cuh): epoch = the token-step counter, salt = launch index within the step;
     // WMAR_LL=0 falls back to the counter hand-off (A/B runs)
     static const bool ll_on = []() { const char *e = getenv("WMAR_LL"); return !(e && e[0] == '0'); }();
+    WMAR_REQUIRE(4 * c.n_layer + 1 < 1024, "too many GEMM launches per step for the hand-off flag");
     unsigned salt = 0;
     auto ll = [&](GemmArgs &q) { if (ll_on) { q.ll_epoch = g->step; q.ll_salt = ++salt; } };
     for (int l = 0; l < (g->fused ? 0 : c.n_layer); l++) {
