@@ -137,15 +137,20 @@ __global__ void __launch_bounds__(256) rar_embed_kernel(const RarCall *cp, const
 }
 
 // One CTA per (head, row): LayerNorm(q), LayerNorm(k_new) over head_dim, append k,v at slot i, attend over 0..i.
-__global__ void __launch_bounds__(RAR_ATT_THREADS) rar_attn_kernel(const float *__restrict__ qkv, int d, int H, int hd, int T,
+// qkv / the caches are NOT __restrict__: loads through read-only (__restrict__ const) pointers may be hoisted above
+// griddepcontrol.wait, i.e. read q,k,v before the producing GEMM has written them (seen in gpt.cu).
+__global__ void __launch_bounds__(RAR_ATT_THREADS) rar_attn_kernel(const float *qkv, int d, int H, int hd, int T,
                                                                    const float *__restrict__ qn_g, const float *__restrict__ qn_b,
                                                                    const float *__restrict__ kn_g, const float *__restrict__ kn_b,
-                                                                   float *__restrict__ kcache, float *__restrict__ vcache,
+                                                                   float *kcache, float *vcache,
                                                                    int layer, const int *pos, float *__restrict__ y) {
     __shared__ float sq[128];
     __shared__ float sc[1280];
     __shared__ float part[8][128];
     __shared__ float red[8];
+    // programmatic dependent launch: the proj GEMM may start (and request its first weights) while this kernel runs
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // qkv comes from the previous kernel
     const int h = blockIdx.x, r = blockIdx.y, i = *pos;
     if (i >= T) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -361,9 +366,20 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
         a.mod_shift = mod; a.mod_scale = mod + d; a.ld_mod = 6 * d;
         ll(a);
         if ((rc = launch_skinny_gemm(PRO_ADALN, EPI_STORE, a, s))) return rc;
-        rar_attn_kernel<<<dim3(H, 2 * B), RAR_ATT_THREADS, 0, s>>>(g->qkv, d, H, g->hd, g->T, L.qn_g, L.qn_b, L.kn_g, L.kn_b,
-                                                                  g->kcache, g->vcache, l, g->pos, g->y);
-        WMAR_LAUNCH_CHECK();
+        {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)H, (unsigned)(2 * B), 1);
+            cfg.blockDim = dim3(RAR_ATT_THREADS, 1, 1);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rar_attn_kernel, (const float *)g->qkv, d, H, g->hd, g->T,
+                                               (const float *)L.qn_g, (const float *)L.qn_b, (const float *)L.kn_g, (const float *)L.kn_b,
+                                               g->kcache, g->vcache, l, (const int *)g->pos, g->y));
+        }
         GemmArgs p{};
         p.ws = g->ws; p.counters = g->counters;
         p.X = g->y; p.ldx = d; p.W = L.wproj; p.bias = L.bproj; p.Y = g->x; p.ldy = d; p.N = d; p.K = d;
