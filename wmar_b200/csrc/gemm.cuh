@@ -12,7 +12,8 @@
 //   * products are 3xTF32 (hi*hi + hi*lo + lo*hi with fp32 accumulation): fp32-faithful results, which the
 //     reference's fp32 (TF32-off) Linear layers require for greedy token parity,
 //   * split-K across CTAs (grid.y) fills all 148 SMs even for N = 1536; partial tiles go to an L2-resident workspace
-//     and the LAST CTA to arrive for a tile reduces them in split order (deterministic) and runs the epilogue,
+//     as {value, flag} words and the CTA of the last split sums them in split order (deterministic) and runs the
+//     epilogue -- no fence, no atomic (GemmArgs::ll_salt; the counter-based last-arriver hand-off is kept as ll_salt = 0),
 //   * LayerNorm / adaLN-modulate are applied to X on the fly (prologue) from per-row statistics that the producing
 //     GEMM's epilogue emitted as (mean, M2) partials per 64-column tile, combined with Chan's formula.
 #pragma once

@@ -6,15 +6,16 @@
 // output to bf16 and every activation it reads is a bf16 tensor.  The engine keeps its activations in fp32 buffers
 // (one code path with the fp32 models) but rounds at exactly those points, so the products are bf16 x bf16 with fp32
 // accumulation like the reference's cuBLAS calls.
-//   * the 16 rows (f | i | u guided row groups of <= 5 images) are the M of mma.m16n8k16; W rows are the MMA's n, and W
-//     goes HBM -> registers as B fragments with no shared-memory staging: one LDG.128 per lane = 8 consecutive k of
-//     one weight row = the B fragments of two k16 MMAs (k permuted identically in the A fragments),
+//   * the 16 rows (f | i | u guided row groups of <= 5 images) are the M of mma.m16n8k16; W rows are the MMA's n, and
+//     every lane fetches exactly the 16-byte pieces that are ITS B fragments: 8 consecutive k of one weight row = the
+//     B fragments of two k16 MMAs (k permuted identically in the A fragments),
 //   * a PERSISTENT grid (two CTAs per SM) walks the (tile, split) work items: the 7B shapes give 256..2048 items, so a
 //     one-item-per-CTA launch would run 1.2-3.5 waves with a ragged tail; the weights travel through the per-lane
 //     cp.async ring of gemm.cuh (three iterations of every warp in flight) and the first three iterations of a CTA's
 //     NEXT item are issued before the split-K tail / epilogue of the current one, so the HBM stream does not drain
 //     inside a kernel,
-//   * split-K with the deterministic last-arriver reduction of gemm.cuh,
+//   * split-K with the flag-carrying hand-off of gemm.cuh ({value, flag} words, summed in split order by the CTA that
+//     owns the last split's item; the counter-based last-arriver reduction remains for ll_salt = 0, e.g. the unit test entry),
 //   * prologues: RMSNorm (xformers RMSNorm, transformer.py:238-239,278) from the producer's (mean, M2) partials;
 //     SwiGLU  silu(x1) * x3  over the two halves of the w13 output (transformer.py:217-218),
 //   * epilogues: round to bf16; residual add (round, add, round) + LayerNorm-style (mean, M2) partials for the next RMS;
