@@ -402,7 +402,8 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
     static const bool ll_on = []() { const char *e = getenv("WMAR_LL"); return !(e && e[0] == '0'); }();
     WMAR_REQUIRE(4 * c.n_layer + 1 < 1024, "too many GEMM launches per step for the hand-off flag");
     unsigned salt = 0;
-    auto ll = [&](GemmArgs &q) { if (ll_on) { q.ll_epoch = g->step; q.ll_salt = ++salt; } };
+    // (not on the fused path: there the block kernels fill the same workspace with raw fp32 partials every step)
+    auto ll = [&](GemmArgs &q) { if (ll_on && !g->fused) { q.ll_epoch = g->step; q.ll_salt = ++salt; } };
     for (int l = 0; l < (g->fused ? 0 : c.n_layer); l++) {
         const Layer &L = g->layers[l];
         GemmArgs a{};
