@@ -112,3 +112,15 @@ def test_state_module_keeps_reference_keys_and_applies_deltas(tmp_path):
     before = m.encoder.conv_in.weight.clone()
     update_weights(m.encoder, str(p))
     assert torch.allclose(m.encoder.conv_in.weight, before + 1.0)
+
+
+def test_split_k_handoff_flags_are_unique_per_generation():
+    """csrc/gemm.cuh: flag = (epoch + 1) * 1024 + salt with salt = 1-based launch index within the step.  The engines
+    clear the workspace at the start of a generation, so within one generation no two launches may share a flag, no flag
+    may be 0 (cleared memory) and all must fit 32 bits -- for the launch counts the three engines produce."""
+    cases = {"taming": (256, 4 * 48 + 1), "rar_xl": (257, 5 * 32 + 2), "anole_7b": (2048, 4 * 32 + 1)}
+    for name, (steps, launches) in cases.items():
+        assert launches < 1024, name
+        flags = {(epoch + 1) * 1024 + salt for epoch in range(steps) for salt in range(1, launches + 1)}
+        assert len(flags) == steps * launches, name
+        assert min(flags) > 0 and max(flags) < 2 ** 32, name
