@@ -124,3 +124,25 @@ def test_split_k_handoff_flags_are_unique_per_generation():
         flags = {(epoch + 1) * 1024 + salt for epoch in range(steps) for salt in range(1, launches + 1)}
         assert len(flags) == steps * launches, name
         assert min(flags) > 0 and max(flags) < 2 ** 32, name
+
+
+def test_psnr_and_l0_follow_the_reference_definitions():
+    """wmar/utils/metrics.py:19-21,34 + utils.py:69-80 restated in numpy (images go through chw_to_pillow = clip + ROUND to
+    uint8 before the PSNR) against wmar_b200.evaluate on CPU tensors, including values that sit on .5 boundaries."""
+    import numpy as np
+    import torch
+    from wmar_b200.evaluate import psnr_uint8, to_uint8
+
+    def ref_u8(x):                       # chw_to_pillow without the PIL container
+        y = (255 * ((x.transpose(1, 2, 0) + 1.0) / 2.0)).clip(0, 255)
+        return np.round(y).astype(np.uint8)
+
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(3, 3, 16, 16, generator=g) * 2.4 - 1.2          # some values outside [-1, 1]
+    b = (a + 0.05 * torch.randn(3, 3, 16, 16, generator=g))
+    a[0, 0, 0, :8] = torch.tensor([(2 * k + 1) / 255.0 - 1.0 for k in range(8)])   # exactly k + 0.5 after rescaling
+    for i in range(3):
+        np.testing.assert_array_equal(to_uint8(a[i:i + 1])[0].permute(1, 2, 0).numpy(), ref_u8(a[i].numpy()))
+        ra, rb = ref_u8(a[i].numpy()), ref_u8(b[i].numpy())
+        mse = np.mean((ra * 1.0 - rb * 1.0) ** 2)
+        assert abs(float(psnr_uint8(a[i:i + 1], b[i:i + 1])[0]) - 10 * np.log10(255.0 ** 2 / mse)) < 1e-9

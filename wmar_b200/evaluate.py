@@ -36,10 +36,14 @@ def fill_batch_log(batch_log, key, model, codes, eval_params, to_numpy=False):
     return batch_log
 
 
+def to_uint8(x):
+    """wmar/utils/utils.py:69-80 chw_to_pillow on a batch: 255 * (x + 1) / 2 in fp32, clip to [0, 255], round half to even."""
+    return torch.round((255 * ((x.float() + 1.0) / 2.0)).clamp(0, 255)).to(torch.uint8)
+
+
 def psnr_uint8(a, b):
-    """compute_psnr on the 8-bit images the reference converts to (chw_to_pillow: clamp, *255, uint8): a, b in [-1,1]."""
-    qa = ((a.clamp(-1, 1) / 2.0 + 0.5) * 255.0).to(torch.uint8).double()
-    qb = ((b.clamp(-1, 1) / 2.0 + 0.5) * 255.0).to(torch.uint8).double()
+    """compute_psnr (metrics.py:19-21) on the 8-bit images the reference converts to (chw_to_pillow); a, b in [-1,1]."""
+    qa, qb = to_uint8(a).double(), to_uint8(b).double()
     mse = (qa - qb).pow(2).flatten(1).mean(dim=1)
     return 10.0 * torch.log10(255.0 ** 2 / mse)
 
