@@ -1,6 +1,7 @@
 """CPU: host-side logic that mirrors the reference (batching / chunking / output tree, generate.py:79-108,179-207),
 the C-ABI exports, and the product path's refusal to run without CUDA."""
 import ctypes
+import json
 import os
 import re
 
@@ -146,3 +147,62 @@ def test_psnr_and_l0_follow_the_reference_definitions():
         ra, rb = ref_u8(a[i].numpy()), ref_u8(b[i].numpy())
         mse = np.mean((ra * 1.0 - rb * 1.0) ** 2)
         assert abs(float(psnr_uint8(a[i:i + 1], b[i:i + 1])[0]) - 10 * np.log10(255.0 ** 2 / mse)) < 1e-9
+
+
+def test_full_mode_writes_the_reference_evaluation_tree(tmp_path):
+    """generate.py:37-108,111-164 with stand-in model / watermarker objects on the CPU: one png + npy + json per
+    (image, transform, parameter), the reference's names, metric keys and metric definitions; --orig_only tree."""
+    import torch
+    from wmar_b200.evaluate import fill_batch_log
+    from wmar_b200.generate import save_batch_log
+
+    class Model:                      # codes <-> images: a fixed invertible toy mapping (4 codes -> 2x2 image)
+        def codes_to_images(self, codes):
+            x = (codes.float() / 7.0 * 2.0 - 1.0).reshape(-1, 1, 2, 2).repeat(1, 3, 1, 1)
+            return x.clamp(-1, 1)
+
+        def images_to_codes(self, imgs):
+            return torch.round((imgs[:, 0].reshape(-1, 4) + 1.0) / 2.0 * 7.0).long().clamp(0, 7)
+
+    class WM:
+        device = "cpu"
+
+        def detect(self, codes):
+            return (codes.sum(dim=1) % 5).double() / 10.0
+
+        def __str__(self):
+            return "linear-stratifiedrand-h=1-d=2.0-g=0.25"
+
+    model, wm = Model(), WM()
+    codes = torch.tensor([[0, 1, 2, 3], [7, 6, 5, 4], [3, 3, 3, 3]])
+    augs = [("brightness", lambda x, b: x * b, [1, 2.0])]
+    ev = {"metric_names": ["pvalue", "l0", "psnr", "bpp"], "augmentations": augs, "max_roundtrips": 1, "orig_only": False}
+    batch = [1, (9, "a prompt"), 1]
+    log = {"batch": batch}
+    fill_batch_log(log, str(wm), model, codes, ev)
+    save_batch_log(log, str(tmp_path), wm, ev, cond_indices=[1, 1, 2])
+    stems = {(1, 1): "c=1,idx=1/0001", (9, 1): "c=9,idx=1/0001", (1, 2): "c=1,idx=2/0002"}
+    expected = set()
+    for stem in stems.values():
+        for tp in ("roundtrips_0", "roundtrips_1", "brightness_1", "brightness_2.0"):
+            for ext in ("png", "npy", "json"):
+                expected.add(f"{stem}_{wm}_{tp}.{ext}")
+    found = {os.path.relpath(os.path.join(d, f), tmp_path) for d, _, fs in os.walk(tmp_path) for f in fs}
+    found = {f.replace(".png.npy", ".png") for f in found}     # save_png falls back to .npy without PIL
+    assert found == expected
+    j0 = json.load(open(tmp_path / f"c=9,idx=1/0001_{wm}_roundtrips_0.json"))
+    assert list(j0) == ["pvalue", "l0", "psnr", "bpp"]
+    assert j0["l0"] == 0.0 and j0["psnr"] == float("inf") and j0["bpp"] is None
+    assert j0["pvalue"] == float(wm.detect(codes)[1])             # detector on the ORIGINAL codes (metrics.py:43)
+    jb = json.load(open(tmp_path / f"c=1,idx=1/0001_{wm}_brightness_2.0.json"))
+    re_codes = model.images_to_codes(((model.codes_to_images(codes) / 2 + 0.5) * 2.0).clamp(0, 1) * 2 - 1)
+    assert jb["l0"] == float((re_codes[0] != codes[0]).sum()) / 4 and jb["pvalue"] == float(wm.detect(re_codes)[0])
+    np.testing.assert_array_equal(np.load(tmp_path / f"c=1,idx=2/0002_{wm}_roundtrips_0.npy"), codes[2].numpy())
+    # --orig_only: images/ + codes/ with "<conditioning>:<idx>" names, no metrics
+    ev0 = {"metric_names": [], "augmentations": [], "max_roundtrips": 0, "orig_only": True}
+    log0 = {"batch": batch}
+    fill_batch_log(log0, str(wm), model, codes, ev0)
+    out0 = tmp_path / "orig"
+    save_batch_log(log0, str(out0), wm, ev0, cond_indices=[1, 1, 2])
+    assert sorted(os.listdir(out0 / "codes")) == ["1:0001.npy", "1:0002.npy", "9:0001.npy"]
+    assert len(os.listdir(out0 / "images")) == 3

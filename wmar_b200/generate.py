@@ -7,9 +7,10 @@
 Same flags, chunking rule (`batch_idx % num_chunks == chunk_id`, seed + 1000 * chunk_id) and output tree as the
 reference.  Under ``torchrun`` every rank is one chunk (chunk_id = RANK, num_chunks = WORLD_SIZE): independent
 images, no data-path collective.  Without --modelpath the models are seeded random-init at the reference's shapes (no
-checkpoints ship with this repo).  Evaluation under augmentations (generate.py:111-164) is outside the hot path: this
-CLI writes the originals (``--orig_only true`` tree) or, in full mode, the ``roundtrips`` entry with the on-device
-detector's metrics (pvalue, l0) per image.
+checkpoints ship with this repo).  Full mode runs the reference's evaluation round trip on the device
+(wmar_b200.evaluate: decode -> [round trip | augment] -> re-encode -> detect) and writes one png / npy / json per
+(image, transform, parameter) exactly like generate.py:37-108; ``--orig_only true`` writes the images/ + codes/ tree.
+The neural-compression and DiffPure transforms (and the ``bpp`` metric they define) are out of scope: ``bpp`` is null.
 """
 import argparse
 import json
@@ -74,6 +75,45 @@ def save_png(path, hwc_uint8):
         Image.fromarray(hwc_uint8).save(path)
     except ImportError:  # PIL is optional here: fall back to a raw .npy next to the expected name
         np.save(path + ".npy", hwc_uint8)
+
+
+def save_batch_log(log, outdir, watermarker, eval_params, cond_indices):
+    """generate.py:37-108 compute_metrics_and_save_from_batch_log: metrics per (method, transform, param, image) and the
+    reference's file names.  The log holds device (or CPU) tensors (wmar_b200.evaluate.fill_batch_log); the metrics of a
+    whole batch are computed at once and only then copied to the host."""
+    from .evaluate import compute_metrics, to_uint8
+    names = list(eval_params["metric_names"])
+    batch = log["batch"]
+    for method in [k for k in log.keys() if k != "batch"]:
+        metrics = compute_metrics(log, method, watermarker, [n for n in names if n != "bpp"])
+        for transform, entries in log[method].items():
+            for e_idx, (param, codes, imgs, _) in enumerate(entries):
+                codes_h = codes.cpu().numpy() if hasattr(codes, "cpu") else np.asarray(codes)
+                u8 = to_uint8(imgs if hasattr(imgs, "cpu") else __import__("torch").as_tensor(imgs)).permute(0, 2, 3, 1).cpu().numpy()
+                m = {n: (v.cpu().tolist() if v is not None else None) for n, v in metrics[transform][e_idx][1].items()}
+                for i in range(len(codes_h)):
+                    conditioning = batch[i]
+                    if hasattr(conditioning, "item"):
+                        conditioning = conditioning.item()
+                    if isinstance(conditioning, tuple):
+                        conditioning = conditioning[0]      # only the index if there is a prompt string too
+                    cond_index = cond_indices[i]
+                    if not eval_params["orig_only"]:
+                        d = os.path.join(outdir, f"c={conditioning},idx={cond_index}")
+                        os.makedirs(d, exist_ok=True)
+                        stem = os.path.join(d, f"{cond_index:04}_{method}_{transform}_{param}")
+                        save_png(stem + ".png", u8[i])
+                        np.save(stem + ".npy", codes_h[i])
+                        row = {n: (None if n == "bpp" or m.get(n) is None else float(m[n][i])) for n in names}
+                        with open(stem + ".json", "w") as f:
+                            json.dump(row, f)
+                    else:
+                        assert param == 0 and transform == "roundtrips"
+                        os.makedirs(os.path.join(outdir, "images"), exist_ok=True)
+                        os.makedirs(os.path.join(outdir, "codes"), exist_ok=True)
+                        suffix = f"_{method}" if len(log.keys()) > 2 else ""
+                        save_png(os.path.join(outdir, "images", f"{conditioning}:{cond_index:04}{suffix}.png"), u8[i])
+                        np.save(os.path.join(outdir, "codes", f"{conditioning}:{cond_index:04}{suffix}.npy"), codes_h[i])
 
 
 def get_parser():
@@ -164,28 +204,19 @@ def main(argv=None):
     model.set_watermarker(watermarker)
     gen_params = {"batch_size": args.batch_size, "temperature": args.temperature, "top_k": args.top_k,
                   "top_p": args.top_p}
-    method = str(watermarker)
+    from wmar_b200.augmentations import default_augmentations
+    from wmar_b200.evaluate import fill_batch_log
+    if args.orig_only:      # generate.py:381-384
+        eval_params = {"metric_names": [], "augmentations": [], "max_roundtrips": 0, "orig_only": True}
+    else:
+        eval_params = {"metric_names": ["pvalue", "l0", "psnr", "bpp"], "augmentations": default_augmentations(),
+                       "max_roundtrips": 1, "orig_only": False}
     n_done = 0
     for batch_idx, batch, cond_indices in plan_batches(all_inputs, args.batch_size, chunk_id, num_chunks):
         codes = model.sample(batch, gen_params, apply_watermark=watermarker is not None)
-        images = model.codes_to_images(codes)
-        stats = None
-        if not args.orig_only:
-            recodes = model.images_to_codes(images)
-            if watermarker is not None:
-                stats = watermarker.detect(recodes).cpu().numpy()
-            l0 = (recodes != codes).float().mean(dim=1).cpu().numpy()
-        codes_h, images_h = codes.cpu().numpy(), images.cpu().numpy()
-        for i, c in enumerate(batch):
-            png, npy, js = output_paths(args.outdir, c, cond_indices[i], method, args.orig_only)
-            os.makedirs(os.path.dirname(png), exist_ok=True)
-            os.makedirs(os.path.dirname(npy), exist_ok=True)
-            save_png(png, chw_to_uint8(images_h[i]))
-            np.save(npy, codes_h[i])
-            if js is not None:
-                m = {"pvalue": float(stats[i]) if stats is not None else 1.0, "l0": float(l0[i])}
-                with open(js, "w") as f:
-                    json.dump(m, f)
+        batch_log = {"batch": batch}
+        fill_batch_log(batch_log, str(watermarker), model, codes, eval_params)
+        save_batch_log(batch_log, args.outdir, watermarker, eval_params, cond_indices)
         n_done += len(batch)
     print(f"[chunk {chunk_id}/{num_chunks}] wrote {n_done} images to {args.outdir}")
     return 0
