@@ -66,6 +66,61 @@ def test_rar_engine_rows_independent_and_watermark_detectable():
     assert st["n_green"].float().mean() > st0["n_green"].float().mean() + 3
 
 
+def test_full_size_rar_xl_vs_oracle():
+    """BASELINE configs[2] shapes (RAR-XL: d=1280, L=32, H=16 -> head_dim 80, mlp 5120, 256 tokens, CFG 4.0) against the
+    CPU oracle, teacher-forced: the engine decodes 8 images (16 guided rows) greedily; the oracle
+    (oracle/rar.py, pinned to the reference's RAR.generate by tests/test_oracle_models.py) is fed the engine's ids for
+    images 0-1 and its guided logits are compared at steps 0-7, 120-127, 248-255: within 1e-3 of the logit range, and
+    the engine's token equals the oracle's arg-max wherever the oracle's own top-1 / top-2
+    gap exceeds 4x the measured error."""
+    from oracle import rar as orar
+    from wmar_b200 import _lib
+    from wmar_b200.models.rar_engine import RAR_SIZES, RAREngine
+    from wmar_b200.models.synthetic import rar_state
+    c = dict(codebook_size=1024, image_seq_len=256, condition_num_classes=1000)
+    c.update(RAR_SIZES["rar_xl"])
+    w = rar_state(c, seed=0, device="cuda")
+    depth, heads = c["num_hidden_layers"], c["num_attention_heads"]
+    eng = RAREngine(w, depth, heads, max_batch=8)
+    cond = torch.tensor([1, 9, 232, 340, 568, 656, 703, 814])
+    steps, R = 256, 2
+    ids, logits = eng.sample(cond, steps, 4.0, 1.0, None, greedy=True, return_logits=True)
+    again = eng.sample(cond, steps, 4.0, 1.0, None, greedy=True)
+    assert torch.equal(ids, again)                                   # deterministic
+    part = eng.sample(cond[:3], steps, 4.0, 1.0, None, greedy=True)
+    assert torch.equal(ids[:3], part)                                # rows independent of the batch they ride in
+    _lib.check(_lib.lib().wmar_check_device_flag(_lib.current_stream()))
+    ids, logits = ids.cpu(), logits[:, :R].cpu()
+    o = orar.RAROracle({k: v.cpu() for k, v in w.items()}, depth, heads)
+    rows = torch.cat([cond[:R] + 1025, torch.full_like(cond[:R], 2025)])
+    check = set(range(0, 8)) | set(range(120, 128)) | set(range(248, 256))
+    worst, decided, undecided, min_gap = 0.0, 0, 0, float("inf")
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        for s in range(steps):
+            last = torch.cat([ids[:R, s - 1], ids[:R, s - 1]]) if s > 0 else None
+            lg = o.step(s, rows, last)
+            if s not in check:
+                continue
+            want = lg[R:] + (lg[:R] - lg[R:]) * 4.0
+            rng = float(want.max() - want.min())
+            err = float((logits[s] - want).abs().max())
+            worst = max(worst, err / rng)
+            assert err <= 1e-3 * rng, (s, err, rng)
+            top2 = want.topk(2, dim=-1).values
+            gap = top2[:, 0] - top2[:, 1]
+            for r in range(R):
+                if float(gap[r]) > 4 * err:
+                    decided += 1
+                    min_gap = min(min_gap, float(gap[r]))
+                    assert int(ids[r, s]) == int(want[r].argmax()), (s, r, float(gap[r]), err)
+                else:
+                    undecided += 1
+    print(f"RAR-XL full-size parity: worst |dlogit|/range = {worst:.2e}; argmax equal on {decided} decided (row, step) "
+          f"pairs (smallest decided gap {min_gap:.3e}), {undecided} pairs inside the error bound")
+    assert decided >= 3 * R * 8 // 4
+
+
 def test_rar_wrapper_surface():
     """RarARMMWrapper.sample / codes_to_images / images_to_codes shapes and ranges at reduced width (full depth of the
     API, not of the model)."""

@@ -116,6 +116,32 @@ def test_taming_full_config_roundtrip():
     assert float(rec.abs().max()) <= 1.0
 
 
+def test_maskgit_full_config_matches_reference_golden():
+    """RAR's tokenizer (MaskGIT-VQGAN, maskgit_vqgan.py:38-361) at the reference's full shapes against the committed
+    golden made by the imported reference modules (oracle/gen_golden.py: maskgit_full): the golden codes of the seeded
+    image (ties only at fp32-rounding distances), and the decoded pixels of the golden codes_in, sub-sampled 8x like
+    the golden, within the 3xTF32 bound -- no oracle involved, reference outputs only."""
+    from wmar_b200.models.vqgan_engine import VQGANEngine
+    ov, ocfg, ecfg, w = _maskgit({}, 5)
+    g = np.load(os.path.join(G, "vqgan.npz"))
+    gen = torch.Generator().manual_seed(13)
+    img = torch.rand(1, 3, 256, 256, generator=gen) * 2 - 1
+    codes_in = torch.randint(0, ocfg["num_embeddings"], (1, 256), generator=gen)
+    np.testing.assert_array_equal(codes_in.numpy(), g["maskgit_full/codes_in"])
+    eng = VQGANEngine(w, ecfg, max_batch=2)
+    codes = eng.encode(img.cuda())
+    z = ov.maskgit_encoder((img + 1) / 2, w, ocfg)
+    emb = w["quantize.embedding.weight"].double()
+    zf = z.permute(0, 2, 3, 1).reshape(-1, emb.shape[1]).double()
+    _check_codes(codes, torch.from_numpy(g["maskgit_full/codes"]).long(),
+                 lambda i, j: float(((zf[i] - emb[j]) ** 2).sum()))
+    rec = eng.decode(codes_in.cuda()).cpu()
+    err = rec[:, :, ::8, ::8] - torch.from_numpy(g["maskgit_full/rec_sub"])
+    assert err.abs().max().item() <= MAX_TOL_3X, err.abs().max().item()
+    assert err.pow(2).mean().sqrt().item() <= RMS_TOL_3X
+    assert float(rec.abs().max()) <= 1.0
+
+
 def test_decode_encode_full_batch_properties():
     """Full-size batch (B=16, config 2's tokenizer load): size-independent properties -- per-row independence from the
     batch composition, determinism, and encode(decode(c)) stability under a second round trip."""

@@ -206,3 +206,16 @@ def test_full_mode_writes_the_reference_evaluation_tree(tmp_path):
     save_batch_log(log0, str(out0), wm, ev0, cond_indices=[1, 1, 2])
     assert sorted(os.listdir(out0 / "codes")) == ["1:0001.npy", "1:0002.npy", "9:0001.npy"]
     assert len(os.listdir(out0 / "images")) == 3
+
+
+def test_chameleon_alive_ids_asset_is_the_reference_key():
+    """The stratified split permutes len(alive) ids, so the alive list is part of the watermark key.  The reference reads
+    assets/chameleon_all_ids.txt (chameleon_wrapper.py:32) with vq.n_e = 8192 (armm_wrapper.py:42-55): 57344 alive BPE
+    ids = [4, 8196) and [16384, 65536), dead = set(range(8192)) - alive = {0, 1, 2, 3}."""
+    from wmar_b200.models.armm_wrapper import load_ids
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    alive = load_ids(os.path.join(here, "wmar_b200", "assets", "chameleon_all_ids.txt"))
+    assert alive == list(range(4, 8196)) + list(range(16384, 65536))
+    assert sorted(set(range(8192)) - set(alive)) == [0, 1, 2, 3]
+    src = open(os.path.join(here, "wmar_b200", "models", "chameleon_wrapper.py")).read()
+    assert "init_alivecodes" in src and "torch.arange(IMAGE_TOKEN_LO" not in src

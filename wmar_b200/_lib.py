@@ -74,6 +74,9 @@ EXPORTS = {
                                        ctypes.c_int64, ctypes.c_int64, c_voidp, c_voidp, c_voidp, c_voidp]),
     "wmar_gpt_algorithmic_bytes": (ctypes.c_double, [c_voidp, ctypes.c_int64, ctypes.c_int64]),
     "wmar_gpt_launches_per_step": (ctypes.c_int, [c_voidp]),
+    "wmar_pstep_prog_bytes": (ctypes.c_int, []),
+    "wmar_pstep_plan_debug": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_voidp,
+                                             ctypes.POINTER(ctypes.c_int)]),
     "wmar_skinny_gemm": (ctypes.c_int, [c_voidp, c_voidp, c_voidp, c_voidp, ctypes.c_int64, ctypes.c_int64,
                                         ctypes.c_int, c_voidp]),
     "wmar_rar_create": (ctypes.c_int, [ctypes.POINTER(RarConfig), ctypes.POINTER(c_voidp), ctypes.c_int,
@@ -146,6 +149,13 @@ def check(rc):
     if rc == -4:
         raise MemoryError(msg)
     raise WmarError(f"wmar_b200 CUDA error ({rc}): {msg}")
+
+
+def check_device_flag():
+    """Reads and clears the current device's error flag (one stream synchronisation).  The product entry points call it
+    once per sample() / detect() so that an out-of-range context id or a top-p overflow raises like the reference's
+    indexing would, instead of yielding silently un-watermarked samples or wrong p-values."""
+    check(lib().wmar_check_device_flag(current_stream()))
 
 
 def ptr(t):

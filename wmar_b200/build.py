@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 SO = os.path.join(HERE, "libwmar_b200.so")
-SOURCES = ["greenlist.cu", "sample.cu", "detect.cu", "gemm.cu", "gemm_tc.cu", "gemm_bf16.cu", "gpt.cu", "rar.cu", "chameleon.cu", "vqgan.cu", "augment.cu"]
+SOURCES = ["greenlist.cu", "sample.cu", "detect.cu", "gemm.cu", "gemm_tc.cu", "gemm_bf16.cu", "gpt.cu", "pstep.cu", "rar.cu", "chameleon.cu", "vqgan.cu", "augment.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-pthread"]
 

@@ -20,6 +20,7 @@
 
 #include "gemm.cuh"
 #include "gpt_fused.cuh"
+#include "pstep_host.h"
 #include "sample.cuh"
 
 using namespace wmar;
@@ -77,6 +78,8 @@ struct wmar_gpt {
     float *ws2;        // second partial buffer (MLP block)
     float *hpart;      // K-split partials of the fc1 tiles
     unsigned *hflag;   // [n_layer][4d/128] arrival counters
+    // persistent step kernel (pstep.cuh): the default path, one launch per token step instead of 5 per layer
+    PstepState *pstep;
 };
 
 namespace {
@@ -369,6 +372,17 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
     const int stat_tiles = d / 64;
     int rc;
     int launches = 0;
+    if (g->pstep) {
+        int *perr = device_err_flag();
+        WMAR_REQUIRE(perr != nullptr, "cannot allocate the device error flag");
+        if ((rc = pstep_enqueue(g->pstep, B, perr, s))) return rc;
+        gpt_sample_kernel<<<B, SAMPLE_THREADS, sample_smem, s>>>(g->d_call, g->logits, g->seq, c.block_size + 1, g->step, perr);
+        WMAR_LAUNCH_CHECK();
+        advance_step_kernel<<<1, 1, 0, s>>>(g->step);
+        WMAR_LAUNCH_CHECK();
+        g->launches_per_step = 3;
+        return WMAR_OK;
+    }
     if (g->fused) {
         const int P_att = (H / 2) * 4, P_mlp = 4 * d / 128;
         for (int l = 0; l < c.n_layer; l++) {
@@ -542,6 +556,7 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
     g->launches_per_step = 5 * cfg->n_layer + 4;
     // fused block kernels whenever the model tiles (WMAR_STEP=graph forces the per-GEMM path)
     g->fused = false; g->ws2 = nullptr; g->hpart = nullptr; g->hflag = nullptr; g->d_trace = nullptr; g->trace_step = -1;
+    g->pstep = nullptr;
     {
         const char *e = getenv("WMAR_STEP_TRACE");
         if (e) {
@@ -556,8 +571,25 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
         }
     }
     {
+        // WMAR_STEP=pstep -> the persistent step kernel (pstep.cuh); default / WMAR_STEP=graph -> per-GEMM graph,
+        // WMAR_STEP=fused -> block kernels.  The default is whichever path measures fastest.
         const char *e = getenv("WMAR_STEP");
-        const bool want_fused = e && e[0] == 'f';   // default: per-GEMM graph path (measured faster, profiles/r01_*)
+        const bool want_pstep = e && e[0] == 'p';
+        if (want_pstep && pstep_eligible(*cfg, g->n_sms)) {
+            std::vector<PstepWeights::Layer> pl((size_t)cfg->n_layer);
+            for (int l = 0; l < cfg->n_layer; l++) {
+                const Layer &Ls = g->layers[l];
+                pl[l] = PstepWeights::Layer{Ls.ln1_g, Ls.ln1_b, Ls.wqkv, Ls.bqkv, Ls.wproj, Ls.bproj, Ls.ln2_g, Ls.ln2_b, Ls.w1, Ls.b1, Ls.w2, Ls.b2};
+            }
+            PstepWeights pw{g->tok_emb, g->pos_emb, g->lnf_g, g->lnf_b, g->head, pl.data()};
+            int prc = pstep_create(*cfg, g->n_sms, pw, g->kcache, g->vcache, g->logits, g->step, g->seq, cfg->block_size + 1, &g->pstep);
+            if (prc != WMAR_OK) { wmar_gpt_destroy(g); return prc; }
+            g->launches_per_step = 3;
+        }
+    }
+    {
+        const char *e = getenv("WMAR_STEP");
+        const bool want_fused = e && e[0] == 'f';   // WMAR_STEP=fused: tcgen05 / cluster block kernels (round 1 experiment)
         if (want_fused && fused_eligible(*cfg)) {
             const size_t P = (size_t)std::max((cfg->n_head / 2) * 4, 4 * d / 128);
             if (ws_floats < P * 16 * d) {
@@ -584,6 +616,7 @@ void wmar_gpt_destroy(wmar_gpt *g) {
     cudaFree(g->kcache); cudaFree(g->vcache); cudaFree(g->ws); cudaFree(g->stats); cudaFree(g->counters);
     cudaFree(g->seq); cudaFree(g->step); cudaFree(g->d_call); cudaFreeHost(g->h_call);
     cudaFree(g->ws2); cudaFree(g->d_trace); cudaFree(g->hpart); cudaFree(g->hflag);
+    pstep_destroy(g->pstep);
     cudaEventDestroy(g->call_done);
     delete g;
 }
@@ -631,14 +664,17 @@ int wmar_gpt_sample(wmar_gpt *g, const wmar_wm_params *wm, const wmar_sample_par
         g->graph_B = (int)B;
     }
     // the step counter restarts at 0: stale {value, flag} words of the previous generation must not match
-    if (!g->fused) WMAR_CUDA_CHECK(cudaMemsetAsync(g->ws, 0, g->ws_bytes, s));
+    if (g->pstep) { if ((rc = pstep_reset(g->pstep, s))) return rc; }
+    else if (!g->fused) WMAR_CUDA_CHECK(cudaMemsetAsync(g->ws, 0, g->ws_bytes, s));
     if (g->fused)
         WMAR_CUDA_CHECK(cudaMemsetAsync(g->hflag, 0, sizeof(unsigned) * (size_t)g->cfg.n_layer * (4 * g->cfg.n_embd / 128), s));
     init_call_kernel<<<1, 32, 0, s>>>(g->d_call, g->seq, g->cfg.block_size + 1, g->step);
     WMAR_LAUNCH_CHECK();
-    embed_kernel<<<16, 256, 0, s>>>(g->d_call, g->seq, g->cfg.block_size + 1, g->step, g->tok_emb, g->pos_emb,
-                                    g->cfg.n_embd, g->cfg.block_size, g->cfg.vocab_size, g->x, g->stats);
-    WMAR_LAUNCH_CHECK();
+    if (!g->pstep) {   // the persistent kernel embeds the token itself
+        embed_kernel<<<16, 256, 0, s>>>(g->d_call, g->seq, g->cfg.block_size + 1, g->step, g->tok_emb, g->pos_emb,
+                                        g->cfg.n_embd, g->cfg.block_size, g->cfg.vocab_size, g->x, g->stats);
+        WMAR_LAUNCH_CHECK();
+    }
     for (int64_t t = 0; t < steps; t++) {
         WMAR_CUDA_CHECK(cudaGraphLaunch(g->exec, s));
         g_launches.fetch_add((uint64_t)g->launches_per_step);
@@ -657,6 +693,12 @@ double wmar_gpt_algorithmic_bytes(const wmar_gpt *g, int64_t B, int64_t steps) {
 }
 
 int wmar_gpt_launches_per_step(const wmar_gpt *g) { return g ? g->launches_per_step : 0; }
+
+/* probe only (WMAR_PSTEP_TRACE): globaltimer stamps of the last token step, [G][512]; returns G or a negative status */
+int wmar_gpt_debug_pstep_trace(const wmar_gpt *g, unsigned long long *out, int64_t cap) {
+    if (!g || !g->pstep || !out) return -1;
+    return pstep_trace(g->pstep, out, (size_t)cap);
+}
 
 /* probe only: copies the [3][48] globaltimer stamps of the traced step to the host */
 int wmar_gpt_debug_trace(const wmar_gpt *g, unsigned long long *out) {

@@ -1,4 +1,6 @@
 // C-ABI entry points for the watermark logit processor and the fused sampling operator.
+#include <mutex>
+
 #include "sample.cuh"
 
 using namespace wmar;
@@ -42,12 +44,26 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) wm_sample_kernel(SampleArgs
     if (threadIdx.x == 0) out_ids[b] = id;
 }
 
-int *g_err_flag = nullptr;  // device int, lazily allocated (per process; one device per process)
+constexpr int MAX_DEVICES = 64;
+int *g_err_flags[MAX_DEVICES] = {};  // one device int per CUDA device, lazily allocated on the device that is current
+std::mutex g_err_mutex;
+
+int *cur_err_flag() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    return g_err_flags[dev];
+}
 
 int ensure_err_flag() {
-    if (g_err_flag == nullptr) {
-        WMAR_CUDA_CHECK(cudaMalloc(&g_err_flag, sizeof(int)));
-        WMAR_CUDA_CHECK(cudaMemset(g_err_flag, 0, sizeof(int)));
+    int dev = 0;
+    WMAR_CUDA_CHECK(cudaGetDevice(&dev));
+    WMAR_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "device index out of range");
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    if (g_err_flags[dev] == nullptr) {
+        int *p = nullptr;
+        WMAR_CUDA_CHECK(cudaMalloc(&p, sizeof(int)));
+        WMAR_CUDA_CHECK(cudaMemset(p, 0, sizeof(int)));
+        g_err_flags[dev] = p;
     }
     return WMAR_OK;
 }
@@ -110,7 +126,7 @@ int wmar_wm_process_logits(const wmar_wm_params *wm, const int64_t *d_past_ids, 
     if (rc) return rc;
     process_logits_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(
         wm->d_table, wm->n_rows, (int)wm->vocab_size, wm->seed_strategy, wm->context_size,
-        wm->spatial_dim > 0 ? wm->spatial_dim : 16, wm->delta, d_past_ids, t, past_stride, d_logits, g_err_flag);
+        wm->spatial_dim > 0 ? wm->spatial_dim : 16, wm->delta, d_past_ids, t, past_stride, d_logits, cur_err_flag());
     WMAR_LAUNCH_CHECK();
     return WMAR_OK;
 }
@@ -130,20 +146,27 @@ int wmar_wm_sample(const wmar_wm_params *wm, const wmar_sample_params *sp, const
     size_t smem = sample_smem_bytes((int)V, a.cand_cap);
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(wm_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wm_sample_kernel<<<(unsigned)B, SAMPLE_THREADS, smem, as_stream(stream)>>>(a, d_logits, d_past_ids, t, past_stride,
-                                                                              d_noise, d_out_ids, g_err_flag);
+                                                                              d_noise, d_out_ids, cur_err_flag());
     WMAR_LAUNCH_CHECK();
     return WMAR_OK;
 }
 
-/* Reads and clears the device error flag (synchronises the stream): 0 ok, bit 0 = context sum outside the greenlist
- * table, bit 1 = more top-p candidates than the shared-memory sorter holds. */
+/* Reads and clears the error flag of the current device (synchronises the stream): 0 ok, bit 0 = context sum outside
+ * the greenlist table, bit 1 = more top-p candidates than the shared-memory sorter holds, bit 2 = a bounded wait of the
+ * persistent step kernel expired. */
 int wmar_check_device_flag(void *stream) {
+    int *g_err_flag = cur_err_flag();
     if (g_err_flag == nullptr) return 0;
     int v = 0;
     WMAR_CUDA_CHECK(cudaMemcpyAsync(&v, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
     WMAR_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
     if (v != 0) {
         WMAR_CUDA_CHECK(cudaMemsetAsync(g_err_flag, 0, sizeof(int), as_stream(stream)));
+        if (v & 4) {
+            char codes[64];
+            snprintf(codes, sizeof(codes), "wait codes 0x%x", (unsigned)v >> 8);
+            return set_error(WMAR_ERR_CUDA, "persistent step kernel: a wait timed out (%s)%s", codes);
+        }
         return set_error(WMAR_ERR_RANGE, "%s%s", (v & 1) ? "context sum outside the greenlist table; " : "",
                          (v & 2) ? "top-p candidate overflow" : "");
     }
@@ -155,6 +178,6 @@ int wmar_check_device_flag(void *stream) {
 namespace wmar {
 int *device_err_flag() {
     if (ensure_err_flag() != WMAR_OK) return nullptr;
-    return g_err_flag;
+    return cur_err_flag();
 }
 }  // namespace wmar

@@ -104,6 +104,7 @@ class ChameleonEngine:
                                                    _lib.ptr(pr), _lib.ptr(plen), p_max, p_max, B, n_groups, float(guidance_text),
                                                    float(guidance_image), steps, _lib.ptr(noise), _lib.ptr(out),
                                                    _lib.ptr(logits), _lib.current_stream()))
+            _lib.check_device_flag()   # raises on an out-of-range context sum / top-p overflow (device-side checks)
         self._keepalive = (pr, plen, noise)
         self.last_n_groups = n_groups
         return (out, logits) if return_logits else out

@@ -14,6 +14,7 @@ vocabulary).  Offline there is neither ``text_tokenizer.json`` nor a checkpoint,
   * the BPE <-> codebook translation of VocabTranslation (vocab.py:76-123, a permutation read from the tokenizer file)
     is a parameter (``bpe2img``); the default is the affine map bpe = code + 4 (image tokens occupy ids 4..8195).
 """
+import os
 import zlib
 
 import torch
@@ -31,6 +32,7 @@ IMAGE_TOKEN_LO, IMAGE_TOKEN_HI = 4, 8196
 END_IMAGE, BEGIN_IMAGE = 8196, 8197
 EOT_ID = 8710            # "<reserved08706>", the <END-OF-TURN> sentinel
 TEXT_LO = 16384
+ASSETS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets")
 
 
 def _stand_in_tokenizer(prompt):
@@ -40,7 +42,7 @@ def _stand_in_tokenizer(prompt):
 class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
     def __init__(self, modelpath=None, *, state_dict=None, tokenizer_state_dict=None, model_cfg=None, vq_cfg=None,
                  tokenize=None, bpe2img=None, device="cuda", max_batch=8, vqgan_precision="3xtf32", seed=0, rng="torch",
-                 guidance_text=3.0, guidance_image=1.2, image_tokens_per_image=1024):
+                 guidance_text=3.0, guidance_image=1.2, image_tokens_per_image=1024, alive_ids_path=None):
         super().__init__()
         self._device = torch.device(device)
         if self._device.type != "cuda":
@@ -67,11 +69,14 @@ class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
                         else torch.arange(n_img) ).to(self._device)          # index: bpe - 4 -> codebook id
         self.img2bpe = torch.empty_like(self.bpe2img)
         self.img2bpe[self.bpe2img] = torch.arange(n_img, device=self._device)
-        # alive ids of the watermark = every BPE id except the four specials below the image tokens
-        # (chameleon_wrapper.py: dead = set(range(8192)) - alive = {0, 1, 2, 3})
+        # alive / dead ids of the watermark exactly as the reference derives them (chameleon_wrapper.py:32 ->
+        # armm_wrapper.py:42-55): alive = the 57344 BPE ids of assets/chameleon_all_ids.txt ([4, 8196) and
+        # [16384, 65536)), dead = set(range(vq.n_e = 8192)) - alive = {0, 1, 2, 3}.  The stratified split permutes
+        # len(alive) ids, so the id list IS part of the watermark key.
+        self.init_alivecodes(alive_ids_path or os.path.join(ASSETS, "chameleon_all_ids.txt"))
         vq = self.tokenizer.quantize
-        vq.alive_ids = torch.arange(IMAGE_TOKEN_LO, self.cfg["vocab_size"], dtype=torch.long)
-        vq.dead_ids = torch.arange(0, IMAGE_TOKEN_LO, dtype=torch.long)
+        if self.cfg["vocab_size"] < 65536:     # reduced test vocabularies only: ids the model cannot emit are dropped
+            vq.alive_ids = vq.alive_ids[vq.alive_ids < self.cfg["vocab_size"]]
         self.codes_size = int(round(image_tokens_per_image ** 0.5))
         self.image_size = self.vq_cfg["resolution"]
         self.dim_z = self.vq_cfg["z_channels"]

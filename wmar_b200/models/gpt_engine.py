@@ -80,6 +80,7 @@ class TamingGPTEngine:
             _lib.check(_lib.lib().wmar_gpt_sample(self.handle, ctypes.byref(wm) if wm is not None else None,
                                                   ctypes.byref(sp), _lib.ptr(cond), B, steps, _lib.ptr(noise),
                                                   _lib.ptr(out), _lib.ptr(logits), _lib.current_stream()))
+            _lib.check_device_flag()   # raises on an out-of-range context sum / top-p overflow (device-side checks)
         self._keepalive = (cond, noise)
         return (out, logits) if return_logits else out
 

@@ -89,6 +89,7 @@ class RAREngine:
                                                   ctypes.byref(sp), _lib.ptr(cond), B, steps, float(guidance_scale),
                                                   _lib.ptr(noise), _lib.ptr(out), _lib.ptr(logits),
                                                   _lib.current_stream()))
+            _lib.check_device_flag()   # raises on an out-of-range context sum / top-p overflow (device-side checks)
         self._keepalive = (cond, noise)
         return (out, logits) if return_logits else out
 

@@ -154,6 +154,7 @@ class GentimeWatermark:
             _lib.check(_lib.lib().wmar_detect(self._params, _lib.ptr(codes), B, L, _lib.ptr(ng), _lib.ptr(ns),
                                               _lib.ptr(z), _lib.ptr(p), _lib.ptr(mask), stride, _lib.ptr(mlen),
                                               _lib.current_stream()))
+            _lib.check_device_flag()   # codes outside the greenlist table raise (the reference's indexing would)
         out = {"n_green": ng, "n_scored": ns, "z": z, "pvalue": p}
         if return_masks:
             lens = mlen.cpu().tolist()
