@@ -148,14 +148,16 @@ double wmar_gpt_algorithmic_bytes(const wmar_gpt *g, int64_t B, int64_t steps);
 /* kernels launched per decode step by this engine */
 int wmar_gpt_launches_per_step(const wmar_gpt *g);
 /*
- * Static work plan of the persistent decode-step kernel (the default Taming path: one launch per token step whose
- * CTAs each stream a fixed share of every weight matrix, csrc/pstep.cuh).  Host logic only, no CUDA call: fills
- * h_progs_out with G records of wmar_pstep_prog_bytes() bytes (layout: csrc/pstep_plan.h PsProg) and h_slots_out[5]
- * with the split-K partial slots of the qkv / proj / fc1 / fc2 / head phases.  Replaces the per-layer launch chain of
- * mingpt.py:183-214; exported so that the plan's invariants are unit-tested without a GPU.
+ * Static work plan of the persistent decode-step kernel (WMAR_STEP=pstep: one launch per token step whose CTAs each
+ * stream a fixed share of every weight matrix, csrc/pstep.cuh).  Host logic only, no CUDA call: fills h_progs_out with
+ * G records of wmar_pstep_prog_bytes() bytes (layout: csrc/pstep_plan.h PsProg) and h_info_out[8] with {Kp, KC, NBn,
+ * stages per packed layer, stages of the packed head, max load, min load, 0}; wmar_pstep_stage_src tells which weights
+ * ring stage `s` of CTA `cta` holds (out4 = {phase or -1 for fc2, n16 tile, k chunk, fc2 n-block}).  Replaces the
+ * per-layer launch chain of mingpt.py:183-214; exported so that the plan's invariants are unit-tested without a GPU.
  */
 int wmar_pstep_prog_bytes(void);
-int wmar_pstep_plan_debug(int G, int d, int H, int V, void *h_progs_out, int *h_slots_out);
+int wmar_pstep_plan_debug(int G, int d, int H, int V, void *h_progs_out, long long *h_info_out);
+int wmar_pstep_stage_src(int G, int d, int H, int V, int cta, int s, int head, int *out4);
 
 /* ------------------------------------------------------------------------------------------------------------
  * RAR decode engine.  Replaces RAR.generate (deps/rar/modeling/rar.py:408-459) + forward_fn (:319-405) + Block /

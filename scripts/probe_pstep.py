@@ -1,6 +1,6 @@
 """Probe of the persistent step kernel at BASELINE configs[1] shapes: decode-loop time per path, ids equality, trace.
 
-    python scripts/probe_pstep.py [steps] [modes...]     (modes: pstep pstep2 graph)
+    python scripts/probe_pstep.py [steps] [modes...]     (modes: pstep graph; WMAR_PSTEP_TRACE=1 prints the phase timeline of the last step)
 """
 import ctypes
 import os
@@ -23,12 +23,9 @@ cond = torch.tensor([1, 9, 232, 340, 568, 656, 703, 814, 937, 975] * 2)[:16]
 out = {}
 for mode in modes:
     os.environ["WMAR_STEP"] = mode[:5]
-    if mode == "pstep2":
-        os.environ["WMAR_PSTEP_NG"] = "2"
     t0 = time.time()
     eng = TamingGPTEngine(w, c["n_layer"], c["n_head"])
     torch.cuda.synchronize()
-    os.environ.pop("WMAR_PSTEP_NG", None)
     print(f"[{mode}] create {time.time() - t0:.2f} s", flush=True)
     ids = eng.sample(cond, steps, 1.0, 250, 0.92, None, greedy=True)
     torch.cuda.synchronize()
@@ -48,37 +45,33 @@ for mode in modes:
     out[mode] = ids.cpu()
     if mode.startswith("pstep") and os.environ.get("WMAR_PSTEP_TRACE"):
         L = _lib.lib()
-        G = 148
-        buf = (ctypes.c_ulonglong * (G * 512))()
+        G, EV = 148, 640
+        buf = (ctypes.c_ulonglong * (G * EV))()
         L.wmar_gpt_debug_pstep_trace.restype = ctypes.c_int
         L.wmar_gpt_debug_pstep_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
-        n = L.wmar_gpt_debug_pstep_trace(eng.handle, buf, G * 512)
+        n = L.wmar_gpt_debug_pstep_trace(eng.handle, buf, G * EV)
         if n > 0:
-            tr = np.frombuffer(buf, dtype=np.uint64).reshape(G, 512)[:n].astype(np.int64)
+            tr = np.frombuffer(buf, dtype=np.uint64).reshape(G, EV)[:n].astype(np.int64)
             t0s = tr[:, 0].min()
-            ev = tr[:, 1:1 + 48 * 5].reshape(n, 48, 5) - t0s
-            end = tr[:, 241] - t0s
-            names = ["qkv+att", "proj", "fc1", "fc2", "-"]
-            print(f"[{mode}] last step: kernel span {end.max() / 1e3:.1f} us; start skew {(tr[:, 0].max() - t0s) / 1e3:.1f} us")
-            prev = np.concatenate([np.zeros((n, 1), dtype=np.int64) + 0, ev[:, :-1, 3]], axis=1)   # end of previous layer
-            for l in (0, 1, 24, 47):
-                seg = []
-                last = prev[:, l] if l > 0 else (tr[:, 0] - t0s)
-                for k in range(4):
-                    seg.append(f"{names[k]} {np.median(ev[:, l, k] - last) / 1e3:5.2f} (max {np.max(ev[:, l, k] - last) / 1e3:5.2f})")
-                    last = ev[:, l, k]
-                print(f"   layer {l:2d}: " + " | ".join(seg) + f" | layer {np.median(ev[:, l, 3] - (prev[:, l] if l else 0)) / 1e3:.1f} us")
-            per_layer = np.diff(np.median(ev[:, :, 3], axis=0))
-            print(f"   median layer period {np.median(per_layer) / 1e3:.2f} us (min {per_layer.min() / 1e3:.2f}, max {per_layer.max() / 1e3:.2f})")
-            it = tr[:, 300:316].reshape(n, 4, 4) - t0s          # [cta][phase][x staged, loop done, reduced, (qkv: attention start)]
-            L2 = c["n_layer"] // 2
-            base = ev[:, L2 - 1, 3]
-            for k, nm in enumerate(["qkv", "proj", "fc1", "fc2"]):
-                st = prev_end = (base if k == 0 else ev[:, L2, k - 1])
-                print(f"   layer {L2} {nm}: phase start -> X staged {np.median(it[:, k, 0] - st) / 1e3:5.2f} (min {np.min(it[:, k, 0] - st) / 1e3:5.2f} max {np.max(it[:, k, 0] - st) / 1e3:5.2f})"
-                      f" | main loop {np.median(it[:, k, 1] - it[:, k, 0]) / 1e3:5.2f} (max {np.max(it[:, k, 1] - it[:, k, 0]) / 1e3:5.2f})"
-                      f" | reduce {np.median(it[:, k, 2] - it[:, k, 1]) / 1e3:5.2f} | hand-off+rest {np.median(ev[:, L2, k] - it[:, k, 2]) / 1e3:5.2f} (max {np.max(ev[:, L2, k] - it[:, k, 2]) / 1e3:5.2f})")
-            print(f"   layer {L2} attention (after last qkv item): {np.median(ev[:, L2, 0] - it[:, 0, 3]) / 1e3:5.2f} us (max {np.max(ev[:, L2, 0] - it[:, 0, 3]) / 1e3:5.2f})")
+            nl = c["n_layer"]
+            ev = (tr[:, 1:1 + nl * 12].reshape(n, nl, 12) - t0s).astype(np.float64) / 1e3
+            ev[tr[:, 1:1 + nl * 12].reshape(n, nl, 12) == 0] = np.nan
+            end = (tr[:, 578] - t0s) / 1e3
+            names = ["x loaded", "qkv done", "qkv flags seen", "attention done", "y loaded", "proj done", "xb loaded",
+                     "fc1 done", "fc2 done", "partials seen", "x reduced"]
+            print(f"[{mode}] last step: kernel span {np.nanmax(end):.1f} us; start skew {(tr[:, 0].max() - t0s) / 1e3:.1f} us; "
+                  f"head starts at {np.nanmedian((tr[:, 577] - t0s) / 1e3):.1f} us")
+            for l in (0, 1, nl // 2, nl - 1):
+                prev = ev[:, l - 1, 10] if l > 0 else np.zeros(n)
+                seg, last = [], prev
+                for k in range(11):
+                    cur = ev[:, l, k]
+                    seg.append(f"{names[k]} +{np.nanmedian(cur - last):5.2f} (max {np.nanmax(cur - last):5.2f})")
+                    last = np.where(np.isnan(cur), last, cur)
+                print(f"   layer {l:2d}: " + " | ".join(seg))
+                print(f"            layer time {np.nanmedian(ev[:, l, 10] - prev):.2f} us (slowest CTA ends {np.nanmax(ev[:, l, 10]) - np.nanmin(prev):.2f} us after the fastest start)")
+            per_layer = np.diff(np.nanmedian(ev[:, :, 10], axis=0))
+            print(f"   median layer period {np.median(per_layer):.2f} us (min {per_layer.min():.2f}, max {per_layer.max():.2f})")
             np.save(os.path.join("gpurun_out", f"pstep_trace_{mode}.npy"), tr)
     del eng
     torch.cuda.empty_cache()

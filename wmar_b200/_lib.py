@@ -76,7 +76,8 @@ EXPORTS = {
     "wmar_gpt_launches_per_step": (ctypes.c_int, [c_voidp]),
     "wmar_pstep_prog_bytes": (ctypes.c_int, []),
     "wmar_pstep_plan_debug": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_voidp,
-                                             ctypes.POINTER(ctypes.c_int)]),
+                                             ctypes.POINTER(ctypes.c_longlong)]),
+    "wmar_pstep_stage_src": (ctypes.c_int, [ctypes.c_int] * 7 + [ctypes.POINTER(ctypes.c_int)]),
     "wmar_skinny_gemm": (ctypes.c_int, [c_voidp, c_voidp, c_voidp, c_voidp, ctypes.c_int64, ctypes.c_int64,
                                         ctypes.c_int, c_voidp]),
     "wmar_rar_create": (ctypes.c_int, [ctypes.POINTER(RarConfig), ctypes.POINTER(c_voidp), ctypes.c_int,

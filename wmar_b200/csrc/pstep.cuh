@@ -1,26 +1,29 @@
 // Persistent decode-step kernel for the Taming minGPT engine: ONE launch runs a whole token step
-// (embedding -> 48 x [LN1+QKV, attention over the KV cache, proj+residual, LN2+fc1+GELU, fc2+residual] -> LN_f + head)
+// (embedding -> L x [LN1+QKV, attention over the KV cache, proj+residual, LN2+fc1+GELU, fc2+residual] -> LN_f + head)
 // replacing the 244 dependent launches per token of the per-GEMM graph (mingpt.py:183-214, 98-122, 42-95).
 //
-// Design (B200 first):
-//   * one CTA per SM (grid = PS_G <= #SMs, all co-resident), 1 producer warp + NG x 4 consumer warps;
-//   * the step is HBM-bound on the weights (5.5 GB / token) and on the K/V cache.  Neither depends on the
-//     activations, so ONE elected producer thread per CTA streams the CTA's static share of every weight matrix
-//     and of the K/V rows of earlier tokens with cp.async.bulk (TMA bulk copies, 16 KB each) into a 10-deep
-//     mbarrier ring (160 KB / SM in flight) and simply keeps going across GEMM and layer boundaries: the stream
-//     never drains while the consumers wait for a dependency;
-//   * weights are re-tiled once at create time (wmar_gpt_create) into 16 KB stages [n64 tile][k64 stage] whose
-//     bytes are already in mma.m16n8k8 B-fragment order for 4 warps x 32 lanes: a stage is one contiguous
-//     bulk copy, and every lane reads its fragments back with conflict-free LDS.128;
-//   * a GEMM phase is cut into (tile, k-range) items, a static share per CTA (pstep_plan.h); the 16 batch rows
-//     are the M of the MMA, products are 3xTF32 with fp32 accumulation (fp32-faithful, as the reference's
-//     TF32-off Linear layers need for greedy token parity), warps split K and reduce through shared memory
-//     in a fixed order, CTAs that share a tile hand their partial to the CTA owning the tile's last k-range;
-//   * every hand-off between CTAs (split-K partials, activations, LayerNorm statistics, q/k/v, attention
-//     output) travels as self-validating {value, flag} 8-byte words (flag = token step and phase): no grid
-//     barrier, no fence, no atomic; a consumer polls exactly the words it needs;
-//   * attention: (head, row) items run on 128-thread warp groups, up to NG at a time per CTA, K then V of the
-//     cached tokens arrive through the same ring; two-pass softmax in shared memory.
+// Design (B200 first; the plan is in pstep_plan.h):
+//   * one CTA per SM (grid G <= #SMs, all co-resident), 1 producer warp + 16 consumer warps;
+//   * the step is HBM-bound on the weights (5.5 GB / token) and on the K/V cache.  Neither depends on the activations,
+//     so ONE elected producer thread per CTA walks the CTA's packed weight stream (contiguous per layer, re-tiled at
+//     create time) and the K/V rows of earlier tokens with cp.async.bulk (TMA bulk copies, 16 KB each) into a 7-deep
+//     mbarrier ring, and asks L2 for the bytes a few hundred KB further down the stream (cp.async.bulk.prefetch.L2):
+//     HBM keeps streaming while the consumers sit in a dependency, the ring then only has to cover the L2 latency.
+//     At the end of a step the prefetch cursor has wrapped into layer 0 of the next token step;
+//   * every GEMM but fc2 is split along N only (a CTA owns n16 tiles with the full K): no split-K partials cross CTAs.
+//     A 16 KB stage is 16 units of n16 x k16 (one per consumer warp, bytes already in mma.m16n8k8 B-fragment order,
+//     read back with two conflict-free LDS.128 per lane); the 16 batch rows are the M of the MMA, products are 3xTF32
+//     with fp32 accumulation (fp32-faithful: the reference's Linear layers run with TF32 off), the 16 warps split K and
+//     are summed in warp order through shared memory (deterministic);
+//   * fc2 is split along K: the CTA keeps its 16 f columns of gelu(fc1) in shared memory and multiplies them with the
+//     matching columns of W2; the [16][d] partials are reduce-scattered through L2 in CTA order, fused with bias +
+//     residual.  fc1 -> fc2 needs no exchange and the 4d-wide hidden activations never leave the SM;
+//   * five exchanges per layer (x -> qkv -> y -> xb -> fc2 partials -> x), each a release/acquire epoch flag per CTA:
+//     writers store plain fp32, bar.sync, one thread fences and stores the flag; one warp of every reader polls the G
+//     flags, fences, bar.sync, then all threads load through L2 (ld.global.cg).  LayerNorm is recomputed by every
+//     consumer CTA from the full row (two-pass, exactly like the reference) -- no statistics exchange;
+//   * attention: (head, row) items on 128-thread warp groups, up to 4 at a time per CTA; K then V of the cached tokens
+//     arrive through the same ring; two-pass softmax in shared memory.
 // All waits are bounded: a wait that exceeds ~1 s raises the device error flag (bit 2) and the kernel drains.
 #pragma once
 #include "gemm.cuh"
@@ -32,18 +35,29 @@ namespace ps {
 
 using namespace tc05;
 
-constexpr int PS_NS = 10;                       // ring depth (stages)
-constexpr int PS_XBUF_BYTES = 65536;            // X slice of an item, later its cross-warp reduction buffer
+constexpr int PS_NW = 16;                       // consumer warps
+constexpr int PS_NT = PS_NW * 32;               // consumer threads
+constexpr int PS_THREADS = PS_NT + 32;          // + the producer warp
+constexpr int PS_NS = 7;                        // ring depth (stages)
+constexpr int PS_DMAX = 1536;                   // widest residual stream whose activations fit beside the ring
+constexpr int PS_XPAD = 16;                     // row stride of X = Kp + 16 floats (== 16 mod 32: conflict-free LDS.128)
+constexpr int PS_HLD = 16 * PS_MAX_F + 16;      // row stride of the gelu(fc1) slice
 constexpr int PS_RING_BYTES = PS_NS * PS_STAGE_BYTES;
-constexpr int PS_OFF_XBUF = PS_RING_BYTES;
-constexpr int PS_OFF_BARS = PS_OFF_XBUF + PS_XBUF_BYTES;     // full[NS], empty[NS]
-constexpr int PS_OFF_STATS = PS_OFF_BARS + 2 * PS_NS * 8;    // float2 row_stats[16]
-constexpr int PS_OFF_DEAD = PS_OFF_STATS + 16 * 8;           // int
+constexpr int PS_OFF_X = PS_RING_BYTES;
+constexpr int PS_X_BYTES = 16 * (PS_DMAX + PS_XPAD) * 4;
+constexpr int PS_OFF_H = PS_OFF_X + PS_X_BYTES;
+constexpr int PS_H_BYTES = 16 * PS_HLD * 4;
+constexpr int PS_OFF_BARS = PS_OFF_H + PS_H_BYTES;          // full[NS], empty[NS]
+constexpr int PS_OFF_DEAD = PS_OFF_BARS + 2 * PS_NS * 8;
 constexpr int PS_SMEM_BYTES = PS_OFF_DEAD + 16;
-constexpr int PS_RED_LD = 72;
 constexpr int PS_ATT_SCRATCH = 8192;            // per warp group: scores[1024], q/k/v[192], part[8][64], red[8]
-constexpr unsigned PS_SPIN_LIMIT = 1u << 24;    // LL polls (~40 ns apart)
+constexpr unsigned PS_SPIN_LIMIT = 1u << 23;    // flag polls (~100 ns apart)
 constexpr unsigned PS_MBAR_LIMIT = 1u << 16;    // try_wait suspends up to 20 us each
+constexpr int PS_TRACE_EV = 640;
+static_assert(PS_SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(4 * PS_ATT_SCRATCH <= PS_X_BYTES && PS_PASS_TILES * 16 * 1024 <= PS_X_BYTES, "scratch aliases X");
+
+enum { FL_X = 0, FL_QKV = 1, FL_ATT = 2, FL_XB = 3, FL_P = 4, FL_N = 5 };
 
 struct PsLayer {
     const float *ln1_g, *ln1_b, *bqkv, *bproj, *ln2_g, *ln2_b, *b1, *b2;
@@ -52,41 +66,64 @@ struct PsLayer {
 struct PsArgs {
     const PsProg *prog;          // [G]
     const PsLayer *layers;       // [L]
-    const uint8_t *wpack;        // [L][layer_bytes] packed qkv | proj | fc1 | fc2
+    const uint8_t *wpack;        // [L][layer_bytes]: per CTA qkv | proj | fc1 | fc2 stages
     unsigned long long layer_bytes;
-    uint32_t ph_off16[4];        // phase base inside a layer block, in 16-byte units
     const uint8_t *head_pack;
     const float *tok_emb, *pos_emb, *lnf_g, *lnf_b;
-    int d, H, V, L, T, B;
+    int d, H, V, L, T, B, G, GP, Kp, KC, NBn;
+    unsigned pf_dist;            // L2 prefetch distance of the weight stream, bytes per CTA
     const int *step;
     const int64_t *seq; int seq_ld;
-    unsigned long long *xa, *xb, *qkv, *y, *h;     // {value, flag} activations [16][ld]
-    ulonglong2 *sta, *stb;                         // LN statistics of xa / xb: [d/64][16] {mean|flag, M2|flag}
-    unsigned long long *ws[PH_N];                  // split-K partial slots [slot][16*64] words
+    float *x, *xb, *y, *qkv;     // plain fp32 activations [16][d], [16][d], [16][d], [16][3d]
+    float *part;                 // fc2 partials [G][16][d]
+    unsigned *flags;             // [FL_N][GP] epoch flags
     float *kcache, *vcache;
-    float *logits;                                 // plain fp32 [16][V]
-    int *abort_flag;                               // global: non-zero = a wait timed out somewhere, drain
-    int *err;                                      // device error flag (bit 2 = pstep timeout)
-    unsigned long long *trace;                     // probe only: [G][PS_TRACE_EV] globaltimer stamps
-    int dbg;
+    float *logits;               // plain fp32 [16][V]
+    int *abort_flag;             // global: non-zero = a wait timed out somewhere, drain
+    int *err;                    // device error flag (bit 2 = pstep timeout)
+    unsigned long long *trace;   // probe only: [G][PS_TRACE_EV] globaltimer stamps
 };
-constexpr int PS_TRACE_EV = 512;
 
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 8, %0;" ::"n"(PS_NT) : "memory"); }
+__device__ __forceinline__ void bar_group(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_cg4(const float *p) {     // L2 only: the line may have been written by another SM
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long timer_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar, uint64_t hint) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(hint) : "memory");
+}
+
 struct Ctx {
     const PsArgs &a;
     uint8_t *smem;
     int *s_dead;
-    unsigned long long *tr_item;   // probe only: stamps inside the GEMM items of one layer
+    unsigned long long *tr;        // probe only
+    int cta;
     __device__ __forceinline__ bool dead() const { return *reinterpret_cast<volatile int *>(s_dead) != 0; }
     __device__ __forceinline__ void timeout(int code) const {
         atomicExch(a.abort_flag, code);
         atomicOr(a.err, 4 | (code << 8));
         *reinterpret_cast<volatile int *>(s_dead) = 1;
     }
-    // periodic check of the global abort flag from inside spin loops
     __device__ __forceinline__ bool poll_abort(unsigned n, unsigned limit, int code) const {
-        if ((n & 255u) == 0u) {
+        if ((n & 63u) == 0u) {
             if (dead()) return true;
             if (*reinterpret_cast<volatile int *>(a.abort_flag) != 0) { *reinterpret_cast<volatile int *>(s_dead) = 1; return true; }
             if (n > limit) { timeout(code); return true; }
@@ -103,442 +140,348 @@ struct Ctx {
             if (n > PS_MBAR_LIMIT) { timeout(code); return; }
         }
     }
+    __device__ __forceinline__ void stamp(int ev) const { if (tr) tr[ev] = timer_ns(); }
 };
 
-template <int NT>
-__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 8, %0;" ::"n"(NT) : "memory"); }
-__device__ __forceinline__ void bar_group(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
-
-__device__ __forceinline__ void ll_load1(const unsigned long long *p, unsigned long long &a) {
-    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
-}
-__device__ __forceinline__ unsigned long long timer_ns() {
-    unsigned long long v;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
-    return v;
-}
-__device__ __forceinline__ void bulk_load_hint(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar, uint64_t hint) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(hint) : "memory");
-}
-
-// 4 consecutive {value, flag} words -> float4 once all four carry `flag`
-__device__ __forceinline__ float4 ll_wait4(const Ctx &c, const unsigned long long *p, uint32_t flag, int code) {
-    unsigned long long q0, q1, q2, q3;
-    unsigned n = 0;
-    while (true) {
-        ll_load2(p, q0, q1);
-        ll_load2(p + 2, q2, q3);
-        if ((uint32_t)(q0 >> 32) == flag && (uint32_t)(q1 >> 32) == flag && (uint32_t)(q2 >> 32) == flag && (uint32_t)(q3 >> 32) == flag) break;
-        if (c.poll_abort(++n, PS_SPIN_LIMIT, code)) break;
-        __nanosleep(32);
+// Release: every consumer thread's global stores of this phase are ordered before the CTA's epoch flag.
+__device__ __forceinline__ void signal_flag(const Ctx &c, int which, unsigned epoch, int ctid) {
+    bar_consumers();
+    if (ctid == 0) {
+        __threadfence();
+        st_relaxed_u32(c.a.flags + which * c.a.GP + c.cta, epoch);
     }
-    return make_float4(__uint_as_float((uint32_t)q0), __uint_as_float((uint32_t)q1), __uint_as_float((uint32_t)q2), __uint_as_float((uint32_t)q3));
 }
-__device__ __forceinline__ void ll_store4(unsigned long long *p, float4 v, uint32_t flag) {
-    ll_store2(p, ll_pack(v.x, flag), ll_pack(v.y, flag));
-    ll_store2(p + 2, ll_pack(v.z, flag), ll_pack(v.w, flag));
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Resolved description of a GEMM phase of layer l at token step t, split so that only the input half is live during
-// the main loop and only the output half during the epilogue.
-struct PhaseIn {
-    const unsigned long long *x; int ldx; uint32_t x_flag;
-    const ulonglong2 *stats_in; const float *ln_g, *ln_b; int K;
-};
-struct PhaseRt {
-    const float *bias; int epi;                                   // 0 store, 1 GELU, 2 residual
-    const unsigned long long *resid; uint32_t resid_flag;
-    unsigned long long *out; int ldo; uint32_t out_flag;         // out == nullptr -> plain logits
-    ulonglong2 *stats_out;
-};
-
-__device__ __forceinline__ uint32_t mkflag(int t, int fid) { return ((uint32_t)(t + 1) << 10) | (uint32_t)fid; }
-// flag ids: 1 = embedding; layer l: 8l+2 qkv, 8l+3 attention, 8l+4 proj, 8l+5 fc1, 8l+6 fc2
-__device__ __forceinline__ int fid_in(int l) { return l == 0 ? 1 : 8 * (l - 1) + 6; }
-
-__device__ __forceinline__ PhaseIn resolve_in(const PsArgs &a, int phase, int l, int t) {
-    PhaseIn r;
-    const int d = a.d;
-    const PsLayer *L = (phase == PH_HEAD) ? nullptr : a.layers + l;
-    r.stats_in = nullptr; r.ln_g = r.ln_b = nullptr; r.K = d; r.ldx = d;
-    switch (phase) {
-    case PH_QKV: r.x = a.xa; r.x_flag = mkflag(t, fid_in(l)); r.stats_in = a.sta; r.ln_g = L->ln1_g; r.ln_b = L->ln1_b; break;
-    case PH_PROJ: r.x = a.y; r.x_flag = mkflag(t, 8 * l + 3); break;
-    case PH_FC1: r.x = a.xb; r.x_flag = mkflag(t, 8 * l + 4); r.stats_in = a.stb; r.ln_g = L->ln2_g; r.ln_b = L->ln2_b; break;
-    case PH_FC2: r.x = a.h; r.ldx = 4 * d; r.K = 4 * d; r.x_flag = mkflag(t, 8 * l + 5); break;
-    default: r.x = a.xa; r.x_flag = mkflag(t, fid_in(l)); r.stats_in = a.sta; r.ln_g = a.lnf_g; r.ln_b = a.lnf_b; break;
-    }
-    return r;
-}
-__device__ __forceinline__ PhaseRt resolve_out(const PsArgs &a, int phase, int l, int t) {
-    PhaseRt r;
-    const int d = a.d;
-    const PsLayer *L = (phase == PH_HEAD) ? nullptr : a.layers + l;
-    r.resid = nullptr; r.resid_flag = 0; r.stats_out = nullptr; r.bias = nullptr; r.epi = 0;
-    switch (phase) {
-    case PH_QKV: r.bias = L->bqkv; r.out = a.qkv; r.ldo = 3 * d; r.out_flag = mkflag(t, 8 * l + 2); break;
-    case PH_PROJ:
-        r.bias = L->bproj; r.epi = 2; r.resid = a.xa; r.resid_flag = mkflag(t, fid_in(l));
-        r.out = a.xb; r.ldo = d; r.out_flag = mkflag(t, 8 * l + 4); r.stats_out = a.stb;
-        break;
-    case PH_FC1: r.bias = L->b1; r.epi = 1; r.out = a.h; r.ldo = 4 * d; r.out_flag = mkflag(t, 8 * l + 5); break;
-    case PH_FC2:
-        r.bias = L->b2; r.epi = 2; r.resid = a.xb; r.resid_flag = mkflag(t, 8 * l + 4);
-        r.out = a.xa; r.ldo = d; r.out_flag = mkflag(t, 8 * l + 6); r.stats_out = a.sta;
-        break;
-    default: r.out = nullptr; r.ldo = a.V; r.out_flag = 0; break;   // PH_HEAD
-    }
-    return r;
-}
-
-// Per-row (mean, rstd) from the producers' per-tile (mean, M2) words; one warp, result in row_stats[16].
-__device__ __forceinline__ void combine_row_stats_ll(const Ctx &c, const ulonglong2 *stats_in, uint32_t flag, int n_tiles, int K,
-                                                     float eps, float2 *row_stats, int lane) {
-    const int r = lane & 15, half = lane >> 4;
-    constexpr int MAXT = 12;
-    float n = 0.f, mean = 0.f, m2 = 0.f;
-    const float w = (float)(K / n_tiles);
-    for (int t0 = 0; t0 < n_tiles; t0 += 2 * MAXT) {
-        float2 sv[MAXT];
+// Acquire: consumer warp 0 polls the G flags of exchange `which` until all carry `epoch` (flags only grow inside a
+// generation), then the whole consumer side synchronises.  Returns with the data of all CTAs visible to ld.global.cg.
+__device__ __forceinline__ void wait_flags(const Ctx &c, int which, unsigned epoch, int ctid, int code) {
+    if (ctid < 32) {
+        const unsigned *f = c.a.flags + which * c.a.GP;
         unsigned spins = 0;
         while (true) {
-            bool ok = true;
-#pragma unroll
-            for (int k = 0; k < MAXT; k++) {
-                const int tl = t0 + half + 2 * k;
-                sv[k] = make_float2(0.f, 0.f);
-                if (tl < n_tiles) {
-                    unsigned long long q0, q1;
-                    ll_load2(reinterpret_cast<const unsigned long long *>(stats_in + tl * 16 + r), q0, q1);
-                    ok = ok && (uint32_t)(q0 >> 32) == flag && (uint32_t)(q1 >> 32) == flag;
-                    sv[k] = make_float2(__uint_as_float((uint32_t)q0), __uint_as_float((uint32_t)q1));
-                }
-            }
-            if (ok) break;
-            if (c.poll_abort(++spins, PS_SPIN_LIMIT, 11)) break;
-            __nanosleep(32);
+            unsigned ok = 1u;
+#pragma unroll 5
+            for (int i = ctid; i < c.a.G; i += 32) ok &= (unsigned)(ld_relaxed_u32(f + i) >= epoch);
+            if (__all_sync(0xffffffffu, ok != 0u)) break;
+            if (c.poll_abort(++spins, PS_SPIN_LIMIT, code)) break;
+            __nanosleep(40);
         }
-        float ms = 0.f, cnt = 0.f;
+        __threadfence();
+    }
+    bar_consumers();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// X[16][Kp] (row stride Kp + 16) <- LayerNorm(src[16][d]) or src itself; warp = row, lane = 4 columns of every 128.
+// mode 0: plain copy, 1: LayerNorm(g, b), 2: embedding tok_emb[id] + pos_emb[t] then LayerNorm (layer 0)
+template <int MODE>
+__device__ __forceinline__ void load_x(const Ctx &c, const float *src, const float *g, const float *b, float eps, int t, int ctid) {
+    const PsArgs &a = c.a;
+    const int row = ctid >> 5, lane = ctid & 31, d = a.d, ldx = a.Kp + PS_XPAD;
+    float *X = reinterpret_cast<float *>(c.smem + PS_OFF_X) + row * ldx;
+    constexpr int MAXI = PS_DMAX / 128;
+    float4 v[MAXI];
+    const float *tok = nullptr, *pos = nullptr;
+    bool active = row < a.B;
+    if (MODE == 2) {
+        long long id = active ? a.seq[(size_t)row * a.seq_ld + t] : 0;
+        if (id < 0 || id >= a.V) id = 0;
+        tok = a.tok_emb + (size_t)id * d;
+        pos = a.pos_emb + (size_t)t * d;
+    }
 #pragma unroll
-        for (int k = 0; k < MAXT; k++)
-            if (t0 + half + 2 * k < n_tiles) { ms += sv[k].x; cnt += 1.f; }
-        const float mloc = cnt > 0.f ? ms / cnt : 0.f;
+    for (int i = 0; i < MAXI; i++) {
+        const int col = i * 128 + lane * 4;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < d && active) {
+            if (MODE == 2) {
+                const float4 e = __ldg(reinterpret_cast<const float4 *>(tok + col));
+                const float4 p = __ldg(reinterpret_cast<const float4 *>(pos + col));
+                v[i] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+            } else {
+                v[i] = ld_cg4(src + (size_t)row * d + col);
+            }
+        }
+    }
+    if (MODE != 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXI; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        const float mean = warp_sum(s) / (float)d;
         float q = 0.f;
 #pragma unroll
-        for (int k = 0; k < MAXT; k++)
-            if (t0 + half + 2 * k < n_tiles) { const float dd = sv[k].x - mloc; q += sv[k].y + w * dd * dd; }
-        chan_combine(n, mean, m2, cnt * w, mloc, q);
+        for (int i = 0; i < MAXI; i++) {
+            const int col = i * 128 + lane * 4;
+            if (col < d) {
+                const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+                q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + eps);
+#pragma unroll
+        for (int i = 0; i < MAXI; i++) {
+            const int col = i * 128 + lane * 4;
+            if (col < d) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4 *>(g + col));
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(b + col));
+                v[i].x = (v[i].x - mean) * rstd * g4.x + b4.x; v[i].y = (v[i].y - mean) * rstd * g4.y + b4.y;
+                v[i].z = (v[i].z - mean) * rstd * g4.z + b4.z; v[i].w = (v[i].w - mean) * rstd * g4.w + b4.w;
+            }
+        }
     }
-    const float nb = __shfl_xor_sync(0xffffffffu, n, 16);
-    const float mb = __shfl_xor_sync(0xffffffffu, mean, 16);
-    const float m2b = __shfl_xor_sync(0xffffffffu, m2, 16);
-    if (half == 0) {
-        chan_combine(n, mean, m2, nb, mb, m2b);
-        row_stats[r] = make_float2(mean, 1.0f / sqrtf(m2 / (float)K + eps));
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) {
+        const int col = i * 128 + lane * 4;
+        if (col < a.Kp) *reinterpret_cast<float4 *>(X + col) = (col < d) ? v[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
-// Epilogue of a finished 16 x 64 output tile: thread (m, nn..nn+3) holds v.
-__device__ __forceinline__ void tile_epilogue(const Ctx &c, const PhaseRt &rt, int tile, int m, int nn, float4 v, int ctid) {
-    const int n = tile * 64 + nn;
-    if (rt.bias != nullptr) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(rt.bias + n));
-        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-    }
-    if (rt.epi == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-    if (rt.epi == 2) {
-        const float4 r4 = ll_wait4(c, rt.resid + (size_t)m * rt.ldo + n, rt.resid_flag, 12);
-        v.x = r4.x + v.x; v.y = r4.y + v.y; v.z = r4.z + v.z; v.w = r4.w + v.w;
-    }
-    if (rt.out != nullptr) ll_store4(rt.out + (size_t)m * rt.ldo + n, v, rt.out_flag);
-    else *reinterpret_cast<float4 *>(c.a.logits + (size_t)m * rt.ldo + n) = v;
-    if (rt.stats_out != nullptr) {
-        float s = v.x + v.y + v.z + v.w;
+// A fragments of one k16 step: rows g and g + 8, four consecutive k per lane (k slot tq <-> k 4tq, tq+4 <-> 4tq+1 in the
+// first MMA, 4tq+2 / 4tq+3 in the second: any bijection works as long as the packed weights use the same one).
+struct XFrag { uint32_t h[2][4], l[2][4]; };
+__device__ __forceinline__ void make_xfrag(XFrag &f, const float4 xa, const float4 xb) {
+    const float r0[4] = {xa.x, xa.y, xa.z, xa.w}, r1[4] = {xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s * (1.0f / 64.0f);
-        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-        float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    for (int e = 0; e < 4; e++) { split_tf32(r0[e], f.h[0][e], f.l[0][e]); split_tf32(r1[e], f.h[1][e], f.l[1][e]); }
+}
+// acc[u] (16 x 8, n8 tile u of the n16 tile) += X(16 x 16) . W(16 x 16)^T, 3xTF32
+__device__ __forceinline__ void unit_mma(float (&acc)[2][4], const XFrag &x, const uint8_t *wunit, int lane) {
+    const float4 w0 = *reinterpret_cast<const float4 *>(wunit + lane * 16);
+    const float4 w1 = *reinterpret_cast<const float4 *>(wunit + 512 + lane * 16);
+    const float wv[2][4] = {{w0.x, w0.y, w0.z, w0.w}, {w1.x, w1.y, w1.z, w1.w}};
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        if ((ctid & 15) == 0)
-            ll_store2(reinterpret_cast<unsigned long long *>(rt.stats_out + tile * 16 + m), ll_pack(mean, rt.out_flag), ll_pack(q, rt.out_flag));
+    for (int u = 0; u < 2; u++) {
+        uint32_t wh[4], wl[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            wh[e] = __float_as_uint(wv[u][e]) & 0xffffe000u;
+            wl[e] = __float_as_uint(wv[u][e] - __uint_as_float(wh[e]));
+        }
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int e = 2 * half;
+            mma_tf32(acc[u], x.l[0][e], x.l[1][e], x.l[0][e + 1], x.l[1][e + 1], wh[e], wh[e + 1]);
+            mma_tf32(acc[u], x.h[0][e], x.h[1][e], x.h[0][e + 1], x.h[1][e + 1], wl[e], wl[e + 1]);
+            mma_tf32(acc[u], x.h[0][e], x.h[1][e], x.h[0][e + 1], x.h[1][e + 1], wh[e], wh[e + 1]);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// One GEMM item: Y[16][64 of tile] (+)= X[16][k-range] . Wtile^T over nst ring stages starting at ring index gi.
-template <int NG>
-__device__ __forceinline__ void gemm_item(const Ctx &c, const int phase, const int l, const int t, const PsItem it, uint32_t gi, int ctid) {
-    constexpr int NW = NG * 4, NT = NW * 32;
-    const int lane = ctid & 31, cw = ctid >> 5, group = cw >> 2, wg = cw & 3;
-    const int g = lane >> 2;
-    const int nst = it.nst, k0 = it.k0st * 64;
-    uint8_t *xbuf = c.smem + PS_OFF_XBUF;
-    float2 *row_stats = reinterpret_cast<float2 *>(c.smem + PS_OFF_STATS);
+// One K-type GEMM phase of this CTA: Y[16][its n16 tiles] = X[16][Kp] . W^T (+ epilogue), in passes of <= 4 tiles.
+// Stage order inside a pass: k chunk major, tile minor (the X fragments of a chunk are split once and reused).
+// EPI 0: + bias -> qkv (global)   1: + bias + residual -> xb (global)   2: + bias, GELU -> gelu slice (shared)   3: -> logits
+template <int EPI>
+__device__ __forceinline__ void gemm_phase(const Ctx &c, const PsProg &pg, int ph, int l, int t, uint32_t &gi, int ctid,
+                                           const float *bias, bool reload_ln) {
+    const PsArgs &a = c.a;
+    const int lane = ctid & 31, cw = ctid >> 5, g = lane >> 2, tq = lane & 3;
+    const int nt = pg.n_tiles[ph], ldx = a.Kp + PS_XPAD;
     const uint32_t full0 = smem_u32(c.smem + PS_OFF_BARS), empty0 = full0 + PS_NS * 8;
-
-    // ---- 1. stage the X slice (16 x nst*64 fp32) into shared memory in A-fragment order, LayerNorm applied
-    bar_consumers<NT>();                     // the previous user of xbuf (reduction buffer / attention scratch) is done
-    {
-    const PhaseIn rt = resolve_in(c.a, phase, l, t);
-    // 1a. LIGHT wait for the producers of this K slice.  Polling the slice itself from every thread saturated L2
-    // (measured: 17-19 us per LN phase); instead one word per source is polled -- the LayerNorm statistics (written
-    // after the tile's values, needed anyway) or the last word of each source (tile, row) -- and the slice is then
-    // loaded once, every word still verified by its own flag (a miss only costs a retry).
-    if (rt.stats_in != nullptr) {
-        if (cw == 0) combine_row_stats_ll(c, rt.stats_in, rt.x_flag, rt.K / 64, rt.K, 1e-5f, row_stats, lane);
-    } else {
-        // attention output rows come from 16 different CTAs per tile; a GEMM-produced tile from one CTA (row 15 = its last warp)
-        const int rows_mode = (phase == PH_PROJ) ? 16 : 1;
-        if (ctid < nst * rows_mode) {
-            const int ti = ctid / rows_mode, row = rows_mode == 16 ? (ctid & 15) : 15;
-            const unsigned long long *p = rt.x + (size_t)row * rt.ldx + k0 + ti * 64 + 63;
-            unsigned long long q;
-            unsigned n = 0;
-            while (true) {
-                ll_load1(p, q);
-                if ((uint32_t)(q >> 32) == rt.x_flag) break;
-                if (c.poll_abort(++n, PS_SPIN_LIMIT, 19)) break;
-                __nanosleep(64);
-            }
+    const float *X = reinterpret_cast<const float *>(c.smem + PS_OFF_X);
+    float *red = reinterpret_cast<float *>(c.smem + PS_OFF_X);
+    for (int t0 = 0; t0 < nt; t0 += PS_PASS_TILES) {
+        const int np = min(PS_PASS_TILES, nt - t0);
+        if (t0 > 0) {
+            // the reduction scratch of the previous pass overwrote X: build it again (head only at full size)
+            bar_consumers();
+            if (reload_ln) load_x<1>(c, a.x, a.lnf_g, a.lnf_b, 1e-5f, t, ctid);
+            bar_consumers();
         }
-    }
-    bar_consumers<NT>();
-    {
-        const int per_row = nst * 16;        // float4 chunks per row
-        const int total = per_row * 16;
-        for (int q0 = ctid; q0 < total; q0 += 4 * NT) {
-            float4 xv[4];
-            int rr[4], kk[4];
+        float acc[PS_PASS_TILES][2][4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int q = q0 + u * NT;
-                rr[u] = q / per_row; kk[u] = (q - rr[u] * per_row) * 4;
-            }
-            // all loads of the batch in flight, then verify; on a miss the whole batch is re-read
-            unsigned spins = 0;
-            while (true) {
-                unsigned long long w[4][4];
+        for (int i = 0; i < PS_PASS_TILES; i++)
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (q0 + u * NT < total) {
-                        const unsigned long long *p = rt.x + (size_t)rr[u] * rt.ldx + k0 + kk[u];
-                        ll_load2(p, w[u][0], w[u][1]);
-                        ll_load2(p + 2, w[u][2], w[u][3]);
-                    }
-                bool ok = true;
+            for (int u = 0; u < 2; u++)
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (q0 + u * NT < total) {
-                        ok = ok && (uint32_t)(w[u][0] >> 32) == rt.x_flag && (uint32_t)(w[u][1] >> 32) == rt.x_flag &&
-                             (uint32_t)(w[u][2] >> 32) == rt.x_flag && (uint32_t)(w[u][3] >> 32) == rt.x_flag;
-                        xv[u] = make_float4(__uint_as_float((uint32_t)w[u][0]), __uint_as_float((uint32_t)w[u][1]),
-                                            __uint_as_float((uint32_t)w[u][2]), __uint_as_float((uint32_t)w[u][3]));
-                    }
-                if (ok) break;
-                if (c.poll_abort(++spins, PS_SPIN_LIMIT, 13)) break;
-                __nanosleep(64);
+                for (int e = 0; e < 4; e++) acc[i][u][e] = 0.f;
+        for (int kc = 0; kc < a.KC; kc++) {
+            XFrag xf;
+            {
+                const float *xp = X + g * ldx + kc * PS_KS + cw * 16 + 4 * tq;
+                make_xfrag(xf, *reinterpret_cast<const float4 *>(xp), *reinterpret_cast<const float4 *>(xp + 8 * ldx));
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (q0 + u * NT < total) {
-                    float4 v = xv[u];
-                    if (rt.stats_in != nullptr) {
-                        const float2 st = row_stats[rr[u]];
-                        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(rt.ln_g + k0 + kk[u]));
-                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(rt.ln_b + k0 + kk[u]));
-                        v.x = (v.x - st.x) * st.y * g4.x + b4.x; v.y = (v.y - st.x) * st.y * g4.y + b4.y;
-                        v.z = (v.z - st.x) * st.y * g4.z + b4.z; v.w = (v.w - st.x) * st.y * g4.w + b4.w;
-                    }
-                    // chunk (k16) c16, quad tq inside it; rows 0-7 in the first 512 bytes of the chunk, 8-15 in the second
-                    const int c16 = kk[u] >> 4, tq = (kk[u] >> 2) & 3;
-                    *reinterpret_cast<float4 *>(xbuf + c16 * 1024 + (rr[u] >> 3) * 512 + ((rr[u] & 7) * 4 + tq) * 16) = v;
-                }
-        }
-    }
-    }
-    bar_consumers<NT>();
-    if (c.tr_item && ctid == 0) c.tr_item[phase * 4 + 0] = timer_ns();
-
-    // ---- 2. main loop: this warp group takes every NG-th stage, each warp one k16 chunk of it
-    float acc[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) acc[j][e] = 0.f;
-    for (int s = group; s < nst; s += NG) {
-        const uint32_t gs = gi + (uint32_t)s, slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
-        c.mbar_wait_b(full0 + slot * 8, parity, 14);
-        const uint8_t *src = c.smem + slot * PS_STAGE_BYTES + wg * 4096 + lane * 16;
-        const float4 xa = *reinterpret_cast<const float4 *>(xbuf + (s * 4 + wg) * 1024 + lane * 16);
-        const float4 xb = *reinterpret_cast<const float4 *>(xbuf + (s * 4 + wg) * 1024 + 512 + lane * 16);
-        const float xs[2][4] = {{xa.x, xa.y, xa.z, xa.w}, {xb.x, xb.y, xb.z, xb.w}};
-        uint32_t xh[2][4], xl[2][4];
-#pragma unroll
-        for (int r = 0; r < 2; r++)
-#pragma unroll
-            for (int e = 0; e < 4; e++) split_tf32(xs[r][e], xh[r][e], xl[r][e]);
-#pragma unroll
-        for (int jh = 0; jh < 2; jh++) {     // two halves of four n8 tiles: 16 weight registers live at a time
-            float4 wcur[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) wcur[j] = *reinterpret_cast<const float4 *>(src + (jh * 4 + j) * 512);
-            if (jh == 1) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty0 + slot * 8);   // the stage's bytes are in registers
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float wv[4] = {wcur[j].x, wcur[j].y, wcur[j].z, wcur[j].w};
-                uint32_t wh[4], wl[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    wh[e] = __float_as_uint(wv[e]) & 0xffffe000u;
-                    wl[e] = __float_as_uint(wv[e] - __uint_as_float(wh[e]));
-                }
-#pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    const int e = 2 * half;
-                    mma_tf32(acc[jh * 4 + j], xl[0][e], xl[1][e], xl[0][e + 1], xl[1][e + 1], wh[e], wh[e + 1]);
-                    mma_tf32(acc[jh * 4 + j], xh[0][e], xh[1][e], xh[0][e + 1], xh[1][e + 1], wl[e], wl[e + 1]);
-                    mma_tf32(acc[jh * 4 + j], xh[0][e], xh[1][e], xh[0][e + 1], xh[1][e + 1], wh[e], wh[e + 1]);
+            for (int i = 0; i < PS_PASS_TILES; i++) {
+                if (i < np) {
+                    const uint32_t gs = gi + (uint32_t)(kc * np + i), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
+                    c.mbar_wait_b(full0 + slot * 8, parity, 14);
+                    unit_mma(acc[i], xf, c.smem + slot * PS_STAGE_BYTES + cw * 1024, lane);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + slot * 8);
                 }
             }
         }
-    }
-
-    // ---- 3. cross-warp reduction in a fixed order (the buffer aliases the X slice)
-    if (c.tr_item && ctid == 0) c.tr_item[phase * 4 + 1] = timer_ns();
-    bar_consumers<NT>();
-    float *red = reinterpret_cast<float *>(xbuf);
-    const int tq = lane & 3;
-    auto red_write = [&](int w) {
-        float *my = red + w * 16 * PS_RED_LD;
+        gi += (uint32_t)(a.KC * np);
+        // cross-warp reduction in warp order; the scratch aliases X
+        bar_consumers();
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            *reinterpret_cast<float2 *>(my + g * PS_RED_LD + 8 * j + 2 * tq) = make_float2(acc[j][0], acc[j][1]);
-            *reinterpret_cast<float2 *>(my + (g + 8) * PS_RED_LD + 8 * j + 2 * tq) = make_float2(acc[j][2], acc[j][3]);
-        }
-    };
-    if (NG == 4) {
-        if (cw >= 8) red_write(cw - 8);
-        bar_consumers<NT>();
-        if (cw < 8) {
-            const float *my = red + cw * 16 * PS_RED_LD;
+        for (int i = 0; i < PS_PASS_TILES; i++) {
+            if (i < np) {
+                float *my = red + ((i * PS_NW + cw) * 16) * 16;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float2 p0 = *reinterpret_cast<const float2 *>(my + g * PS_RED_LD + 8 * j + 2 * tq);
-                const float2 p1 = *reinterpret_cast<const float2 *>(my + (g + 8) * PS_RED_LD + 8 * j + 2 * tq);
-                acc[j][0] += p0.x; acc[j][1] += p0.y; acc[j][2] += p1.x; acc[j][3] += p1.y;
-            }
-            red_write(cw);
-        }
-    } else {
-        red_write(cw);
-    }
-    bar_consumers<NT>();
-    if (ctid >= 256) return;                 // warps 8.. go on to the next item's first barrier
-    const int m = ctid >> 4, nn = (ctid & 15) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        const float4 p = *reinterpret_cast<const float4 *>(red + (w * 16 + m) * PS_RED_LD + nn);
-        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-    }
-
-    // ---- 4. hand-off
-    if (c.tr_item && ctid == 0) c.tr_item[phase * 4 + 2] = timer_ns();
-    unsigned long long *ws = c.a.ws[phase];
-    const uint32_t pflag = resolve_in(c.a, phase, l, t).x_flag;      // unique per (step, layer) inside this phase's slots
-    if (!it.reducer) {
-        ll_store4(ws + (size_t)it.slot * 1024 + m * 64 + nn, v, pflag);
-        return;
-    }
-    if (it.nparts > 0) {
-        const float4 own = v;
-        v = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < it.nparts; s0 += 4) {          // four partials in flight, summed in k order
-            unsigned long long q[4][4];
-            unsigned spins = 0;
-            while (true) {
-                bool ok = true;
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (s0 + k < it.nparts) {
-                        const unsigned long long *src = ws + (size_t)(it.slot + s0 + k) * 1024 + m * 64 + nn;
-                        ll_load2(src, q[k][0], q[k][1]);
-                        ll_load2(src + 2, q[k][2], q[k][3]);
-                    }
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (s0 + k < it.nparts) {
-#pragma unroll
-                        for (int e = 0; e < 4; e++) ok = ok && ((uint32_t)(q[k][e] >> 32) == pflag);
-                    }
-                if (ok) break;
-                if (c.poll_abort(++spins, PS_SPIN_LIMIT, 15)) break;
-                __nanosleep(64);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (s0 + k < it.nparts) {
-                    v.x += __uint_as_float((uint32_t)q[k][0]); v.y += __uint_as_float((uint32_t)q[k][1]);
-                    v.z += __uint_as_float((uint32_t)q[k][2]); v.w += __uint_as_float((uint32_t)q[k][3]);
+                for (int u = 0; u < 2; u++) {
+                    *reinterpret_cast<float2 *>(my + g * 16 + 8 * u + 2 * tq) = make_float2(acc[i][u][0], acc[i][u][1]);
+                    *reinterpret_cast<float2 *>(my + (g + 8) * 16 + 8 * u + 2 * tq) = make_float2(acc[i][u][2], acc[i][u][3]);
                 }
+            }
         }
-        v.x += own.x; v.y += own.y; v.z += own.z; v.w += own.w;
+        bar_consumers();
+        if (ctid < np * 64) {
+            const int i = ctid >> 6, m = (ctid >> 2) & 15, n4 = (ctid & 3) * 4;
+            const int tile = pg.tiles[pg.first[ph] + t0 + i], n = tile * 16 + n4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < PS_NW; w++) {
+                const float4 p = *reinterpret_cast<const float4 *>(red + ((i * PS_NW + w) * 16 + m) * 16 + n4);
+                v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+            }
+            if (bias != nullptr) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + n));
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            }
+            if (EPI == 0) {
+                *reinterpret_cast<float4 *>(a.qkv + (size_t)m * 3 * a.d + n) = v;
+            } else if (EPI == 1) {
+                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (l == 0) {                 // layer 0: the residual is the embedding itself (mingpt.py:186-200)
+                    if (m < a.B) {
+                        long long id = a.seq[(size_t)m * a.seq_ld + t];
+                        if (id < 0 || id >= a.V) id = 0;
+                        const float4 e = __ldg(reinterpret_cast<const float4 *>(a.tok_emb + (size_t)id * a.d + n));
+                        const float4 p = __ldg(reinterpret_cast<const float4 *>(a.pos_emb + (size_t)t * a.d + n));
+                        r4 = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+                    }
+                } else {
+                    r4 = ld_cg4(a.x + (size_t)m * a.d + n);
+                }
+                v.x = r4.x + v.x; v.y = r4.y + v.y; v.z = r4.z + v.z; v.w = r4.w + v.w;
+                *reinterpret_cast<float4 *>(a.xb + (size_t)m * a.d + n) = v;
+            } else if (EPI == 2) {
+                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+                float *hb = reinterpret_cast<float *>(c.smem + PS_OFF_H);
+                *reinterpret_cast<float4 *>(hb + m * PS_HLD + (t0 + i) * 16 + n4) = v;
+            } else {
+                if (m < a.B) *reinterpret_cast<float4 *>(a.logits + (size_t)m * a.V + n) = v;
+            }
+        }
     }
-    tile_epilogue(c, resolve_out(c.a, phase, l, t), it.tile, m, nn, v, ctid);
+}
+
+// fc2 of this CTA: part[cta][16][d] = gelu slice [16][16 f] . W2[:, its 16 f columns]^T.  Stage (nb, j): warp w owns
+// n16 tile nb * 16 + w, k16 step j; a tile is complete after f stages and goes straight from registers to L2.
+__device__ __forceinline__ void fc2_phase(const Ctx &c, const PsProg &pg, uint32_t &gi, int ctid) {
+    const PsArgs &a = c.a;
+    const int lane = ctid & 31, cw = ctid >> 5, g = lane >> 2, tq = lane & 3;
+    const int f = pg.n_tiles[PH_FC1];
+    if (f == 0) return;
+    const uint32_t full0 = smem_u32(c.smem + PS_OFF_BARS), empty0 = full0 + PS_NS * 8;
+    const float *hb = reinterpret_cast<const float *>(c.smem + PS_OFF_H);
+    float *out = a.part + (size_t)c.cta * 16 * a.d;
+    for (int nb = 0; nb < a.NBn; nb++) {
+        float acc[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[u][e] = 0.f;
+        for (int j = 0; j < f; j++) {
+            XFrag xf;
+            const float *xp = hb + g * PS_HLD + j * 16 + 4 * tq;
+            make_xfrag(xf, *reinterpret_cast<const float4 *>(xp), *reinterpret_cast<const float4 *>(xp + 8 * PS_HLD));
+            const uint32_t gs = gi + (uint32_t)(nb * f + j), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
+            c.mbar_wait_b(full0 + slot * 8, parity, 21);
+            unit_mma(acc, xf, c.smem + slot * PS_STAGE_BYTES + cw * 1024, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + slot * 8);
+        }
+        const int n0 = nb * PS_NB + cw * 16;
+        if (n0 < a.d) {
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                *reinterpret_cast<float2 *>(out + (size_t)g * a.d + n0 + 8 * u + 2 * tq) = make_float2(acc[u][0], acc[u][1]);
+                *reinterpret_cast<float2 *>(out + (size_t)(g + 8) * a.d + n0 + 8 * u + 2 * tq) = make_float2(acc[u][2], acc[u][3]);
+            }
+        }
+    }
+    gi += (uint32_t)(a.NBn * f);
+}
+
+// x[slice] = xb[slice] + b2 + sum over CTAs (in CTA order) of their fc2 partials: the reduce-scatter half of fc2.
+__device__ __forceinline__ void reduce_phase(const Ctx &c, const PsProg &pg, const float *b2, int ctid) {
+    const PsArgs &a = c.a;
+    const int n = pg.red_hi - pg.red_lo;             // float4 elements of the flattened [16][d]
+    float4 *scr = reinterpret_cast<float4 *>(c.smem + PS_OFF_X);
+    // thread = (element e, group q): group q sums the partials of CTAs q, q + NQ, ... ; groups are added in q order
+    int NQ = PS_NT / max(n, 1);
+    if (NQ > 8) NQ = 8;
+    if (NQ < 1) NQ = 1;
+    for (int e0 = 0; e0 < n; e0 += PS_NT / NQ) {
+        const int per = PS_NT / NQ;
+        const int e = e0 + ctid % per, q = ctid / per;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n && q < NQ) {
+            const size_t idx = (size_t)(pg.red_lo + e) * 4;
+            // CTAs without fc1 tiles never write their partial: it stays zero from create time
+#pragma unroll 4
+            for (int cc = q; cc < a.G; cc += NQ) {
+                const float4 p = ld_cg4(a.part + (size_t)cc * 16 * a.d + idx);
+                s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+            }
+            scr[q * per + (e - e0)] = s;
+        }
+        bar_consumers();
+        if (e < n && q == 0) {
+            const size_t idx = (size_t)(pg.red_lo + e) * 4;
+            const int col = (int)(idx % (size_t)a.d);
+            float4 v = ld_cg4(a.xb + idx);
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(b2 + col));
+            float4 sum = scr[e - e0];
+            for (int qq = 1; qq < NQ; qq++) {
+                const float4 p = scr[qq * per + (e - e0)];
+                sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+            }
+            v.x += sum.x + b4.x; v.y += sum.y + b4.y; v.z += sum.z + b4.z; v.w += sum.w + b4.w;
+            *reinterpret_cast<float4 *>(a.x + idx) = v;
+        }
+        bar_consumers();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Attention batch: up to NG (head,row) items of this CTA, one per warp group.  K stages then V stages of the cached
-// tokens come through the ring (order: stage-major, item-minor; rows >= B are skipped by producer and consumers alike).
-template <int NG>
+// Attention batch: up to 4 (head,row) items of this CTA, one per warp group.  K stages then V stages of the cached
+// tokens come through the ring (order: K/V major, stage, item minor; rows >= B are skipped by producer and consumers).
 __device__ __forceinline__ uint32_t attn_stage_count(const PsArgs &a, const PsProg &pg, int batch, int t) {
     int nact = 0;
-    for (int i = 0; i < NG; i++) {
-        const int r = batch * NG + i;
+    for (int i = 0; i < 4; i++) {
+        const int r = batch * 4 + i;
         if (r < pg.n_attn && (pg.attn[r] & 15) < a.B) nact++;
     }
     return (uint32_t)(2 * ((t + 63) >> 6) * nact);
 }
 
-template <int NG>
 __device__ __forceinline__ void attn_batch(const Ctx &c, const PsProg &pg, int batch, int l, int t, uint32_t gi, int ctid) {
-    constexpr int NW = NG * 4, NT = NW * 32;
     const PsArgs &a = c.a;
     const int lane = ctid & 31, cw = ctid >> 5, group = cw >> 2, wg = cw & 3;
     const int tid128 = ctid & 127, sub = lane & 15, hf = lane >> 4;
     const uint32_t full0 = smem_u32(c.smem + PS_OFF_BARS), empty0 = full0 + PS_NS * 8;
-    bar_consumers<NT>();                     // xbuf is free
-    const int r = batch * NG + group;
+    const int r = batch * 4 + group;
     if (r >= pg.n_attn) return;
     const int item = pg.attn[r], h = item >> 4, b = item & 15;
+    if (b >= a.B) return;                     // inactive row: y keeps its (finite) old contents, nobody reads the row
     const int d = a.d;
-    const uint32_t out_flag = mkflag(t, 8 * l + 3);
-    unsigned long long *yout = a.y + (size_t)b * d + h * 64;
-    if (b >= a.B) {                           // inactive row: zeros keep the proj GEMM's rows finite
-        if (tid128 < 16) ll_store4(yout + 4 * tid128, make_float4(0.f, 0.f, 0.f, 0.f), out_flag);
-        return;
-    }
     int nact = 0, ai = 0;
-    for (int i = 0; i < NG; i++) {
-        const int rr = batch * NG + i;
+    for (int i = 0; i < 4; i++) {
+        const int rr = batch * 4 + i;
         if (rr < pg.n_attn && (pg.attn[rr] & 15) < a.B) { if (i < group) ai++; nact++; }
     }
     const int nK = (t + 63) >> 6;
-    float *scr = reinterpret_cast<float *>(c.smem + PS_OFF_XBUF + group * PS_ATT_SCRATCH);
+    float *scr = reinterpret_cast<float *>(c.smem + PS_OFF_X + group * PS_ATT_SCRATCH);
     float *sc = scr, *qs = scr + 1024, *kn = scr + 1088, *vn = scr + 1152, *part = scr + 1216, *redv = scr + 1728;
     const size_t cbase = (((size_t)l * 16 + b) * a.H + h) * (size_t)a.T * 64;
 
-    // 1. this step's q, k, v (written by the qkv reducers); k, v are appended to the cache for later steps
+    // 1. this step's q, k, v (written by the qkv tiles' owners); k, v are appended to the cache for later steps
     if (tid128 < 48) {
         const int which = tid128 >> 4, cq = tid128 & 15;
-        const float4 v4 = ll_wait4(c, a.qkv + (size_t)b * 3 * d + which * d + h * 64 + 4 * cq, mkflag(t, 8 * l + 2), 16);
+        const float4 v4 = ld_cg4(a.qkv + (size_t)b * 3 * d + which * d + h * 64 + 4 * cq);
         *reinterpret_cast<float4 *>(scr + 1024 + which * 64 + 4 * cq) = v4;
         if (which == 1) *reinterpret_cast<float4 *>(a.kcache + cbase + (size_t)t * 64 + 4 * cq) = v4;
         if (which == 2) *reinterpret_cast<float4 *>(a.vcache + cbase + (size_t)t * 64 + 4 * cq) = v4;
@@ -565,7 +508,7 @@ __device__ __forceinline__ void attn_batch(const Ctx &c, const PsProg &pg, int b
             if (sub == 0 && j < t) sc[j] = s * scale;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + slot * 8);
+        if (lane == 0) mbar_arrive_cnt(empty0 + slot * 8, 4);
     }
     if (wg == 0) {                             // this step's own key
         const float4 k4 = *reinterpret_cast<const float4 *>(kn + 4 * sub);
@@ -612,7 +555,7 @@ __device__ __forceinline__ void attn_batch(const Ctx &c, const PsProg &pg, int b
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + slot * 8);
+        if (lane == 0) mbar_arrive_cnt(empty0 + slot * 8, 4);
     }
     if (wg == 0 && hf == 0) {
         const float4 v4 = *reinterpret_cast<const float4 *>(vn + 4 * sub);
@@ -629,56 +572,77 @@ __device__ __forceinline__ void attn_batch(const Ctx &c, const PsProg &pg, int b
             o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
         }
         o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
-        ll_store4(yout + 4 * tid128, o, out_flag);
+        *reinterpret_cast<float4 *>(a.y + (size_t)b * d + h * 64 + 4 * tid128) = o;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <int NG>
-__global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) pstep_kernel(const __grid_constant__ PsArgs a) {
-    constexpr int NW = NG * 4, NT = NW * 32;
+__global__ void __launch_bounds__(PS_THREADS, 1) pstep_kernel(const __grid_constant__ PsArgs a) {
     extern __shared__ __align__(1024) uint8_t ps_smem[];
     const int tid = threadIdx.x, cta = blockIdx.x;
     const int t = *a.step;
     if (t >= a.T) return;
     const PsProg &pg = a.prog[cta];
-    Ctx c{a, ps_smem, reinterpret_cast<int *>(ps_smem + PS_OFF_DEAD), nullptr};
+    Ctx c{a, ps_smem, reinterpret_cast<int *>(ps_smem + PS_OFF_DEAD), nullptr, cta};
     const uint32_t full0 = smem_u32(ps_smem + PS_OFF_BARS), empty0 = full0 + PS_NS * 8;
     if (tid == 0) {
-        for (int s = 0; s < PS_NS; s++) { mbar_init(full0 + s * 8, 1); mbar_init(empty0 + s * 8, 4); }
+        for (int s = 0; s < PS_NS; s++) { mbar_init(full0 + s * 8, 1); mbar_init(empty0 + s * 8, PS_NW); }
         *c.s_dead = 0;
         mbar_fence_init();
     }
     __syncthreads();
-    const int n_batches = (pg.n_attn + NG - 1) / NG;
+    const int n_batches = (pg.n_attn + 3) / 4;
+    const unsigned ep0 = (unsigned)t * (unsigned)(a.L + 1) + 1u;      // epoch of (step t, layer 0)
 
     if (tid < 32) {
         // =========================== producer: one thread streams this CTA's weights and K/V ===========================
         if (tid != 0) return;
         uint32_t gi = 0;
+        // L2 prefetch cursor: runs pf_dist bytes ahead of the loads along [layer 0 block | ... | layer L-1 block | head
+        // block] and wraps into layer 0 (= the next token step) at the end
+        int pf_l = 0;
+        unsigned long long pf_off = 0;
+        auto blk_base = [&](int li) -> const uint8_t * {
+            return li < a.L ? a.wpack + (size_t)li * a.layer_bytes + (size_t)pg.layer_off16 * 16 : a.head_pack + (size_t)pg.head_off16 * 16;
+        };
+        auto blk_bytes = [&](int li) -> unsigned long long {
+            return (unsigned long long)(li < a.L ? pg.layer_stages : pg.head_stages) * PS_STAGE_BYTES;
+        };
+        auto prefetch = [&](unsigned long long n) {
+            int guard = 0;
+            while (n > 0 && guard++ < 64) {
+                const unsigned long long left = blk_bytes(pf_l) - pf_off;
+                if (left == 0) { pf_l = (pf_l + 1) % (a.L + 1); pf_off = 0; continue; }
+                const unsigned long long chunk = n < left ? n : left;
+                prefetch_l2_bulk(blk_base(pf_l) + pf_off, (uint32_t)chunk);
+                pf_off += chunk; n -= chunk;
+            }
+        };
+        if (a.pf_dist > 0) for (unsigned long long p = 0; p < a.pf_dist; p += 65536) prefetch(65536);
         auto issue = [&](const void *src, uint32_t bytes) {
             const uint32_t slot = gi % PS_NS;
             if (gi >= PS_NS) c.mbar_wait_b(empty0 + slot * 8, ((gi / PS_NS) - 1u) & 1u, 20);
+            if (c.dead()) return;
             mbar_arrive_expect_tx(full0 + slot * 8, bytes);
             bulk_load_hint(smem_u32(ps_smem + slot * PS_STAGE_BYTES), src, bytes, full0 + slot * 8, L2_EVICT_FIRST);
             gi++;
         };
-        auto issue_items = [&](int phase, const uint8_t *base) {
-            for (int i = 0; i < pg.n_items[phase]; i++) {
-                const PsItem it = pg.items[pg.first[phase] + i];
-                const uint8_t *src = base + (size_t)it.w_off16 * 16;
-                for (int s = 0; s < it.nst; s++) issue(src + (size_t)s * PS_STAGE_BYTES, PS_STAGE_BYTES);
+        auto issue_weights = [&](const uint8_t *&cur, int n) {
+            for (int s = 0; s < n && !c.dead(); s++) {
+                issue(cur, PS_STAGE_BYTES);
+                cur += PS_STAGE_BYTES;
+                if (a.pf_dist > 0) prefetch(PS_STAGE_BYTES);
             }
         };
         const int nK = (t + 63) >> 6;
-        for (int l = 0; l < a.L; l++) {
-            const uint8_t *wl = a.wpack + (size_t)l * a.layer_bytes;
-            issue_items(PH_QKV, wl + (size_t)a.ph_off16[PH_QKV] * 16);
+        for (int l = 0; l < a.L && !c.dead(); l++) {
+            const uint8_t *cur = blk_base(l);
+            issue_weights(cur, pg.n_tiles[PH_QKV] * a.KC);
             for (int bt = 0; bt < n_batches; bt++) {
                 for (int kv = 0; kv < 2; kv++)
                     for (int st = 0; st < nK; st++)
-                        for (int i = 0; i < NG; i++) {
-                            const int r = bt * NG + i;
+                        for (int i = 0; i < 4; i++) {
+                            const int r = bt * 4 + i;
                             if (r >= pg.n_attn) break;
                             const int item = pg.attn[r], h = item >> 4, b = item & 15;
                             if (b >= a.B) continue;
@@ -687,75 +651,152 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) pstep_kernel(const __gri
                             issue((kv == 0 ? a.kcache : a.vcache) + cbase, (uint32_t)rows * 256u);
                         }
             }
-            issue_items(PH_PROJ, wl + (size_t)a.ph_off16[PH_PROJ] * 16);
-            issue_items(PH_FC1, wl + (size_t)a.ph_off16[PH_FC1] * 16);
-            issue_items(PH_FC2, wl + (size_t)a.ph_off16[PH_FC2] * 16);
+            issue_weights(cur, pg.n_tiles[PH_PROJ] * a.KC);
+            issue_weights(cur, pg.n_tiles[PH_FC1] * a.KC);
+            issue_weights(cur, pg.n_tiles[PH_FC1] * a.NBn);
         }
-        issue_items(PH_HEAD, a.head_pack);
+        {
+            const uint8_t *cur = blk_base(a.L);
+            issue_weights(cur, pg.n_tiles[PH_HEAD] * a.KC);
+        }
+        // drain: every issued copy has landed before the CTA may retire (matters only when the consumers bailed out)
+        if (c.dead()) {
+            const uint32_t n_out = gi < PS_NS ? gi : PS_NS;
+            for (uint32_t k = 0; k < n_out; k++) {
+                const uint32_t gs = gi - 1 - k, slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
+                unsigned n = 0;
+                while (!mbar_try_wait(full0 + slot * 8, parity) && ++n < 64) {}
+            }
+        }
         return;
     }
 
     // ================================================ consumers ================================================
     const int ctid = tid - 32;
-    unsigned long long *tr = a.trace ? a.trace + (size_t)cta * PS_TRACE_EV : nullptr;
-    if (tr && ctid == 0) tr[0] = timer_ns();
-    // embedding: x = tok_emb[id] + pos_emb[t] for the tiles of this CTA (mingpt.py:186-200), rows >= B are zero
-    for (int tile = cta; tile < a.d / 64; tile += gridDim.x) {
-        if (ctid < 256) {
-            const int m = ctid >> 4, nn = (ctid & 15) * 4, n = tile * 64 + nn;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < a.B) {
-                long long id = a.seq[(size_t)m * a.seq_ld + t];
-                if (id < 0 || id >= a.V) id = 0;
-                const float4 e = __ldg(reinterpret_cast<const float4 *>(a.tok_emb + (size_t)id * a.d + n));
-                const float4 p = __ldg(reinterpret_cast<const float4 *>(a.pos_emb + (size_t)t * a.d + n));
-                v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
-            }
-            PhaseRt rt{};
-            rt.epi = 0; rt.out = a.xa; rt.ldo = a.d; rt.out_flag = mkflag(t, 1); rt.stats_out = a.sta;
-            tile_epilogue(c, rt, tile, m, nn, v, ctid);
-        }
-    }
+    c.tr = (a.trace && ctid == 0) ? a.trace + (size_t)cta * PS_TRACE_EV : nullptr;
+    c.stamp(0);
     uint32_t gi = 0;
-    // layers 0..L-1 run phases qkv [attention] proj fc1 fc2; "layer" L is the head.  One call site for the GEMM item
-    // and one for the attention batch keep the kernel small (every phase shares the same code).
 #pragma unroll 1
-    for (int l = 0; l <= a.L; l++) {
-        const int ph0 = l < a.L ? PH_QKV : PH_HEAD, ph1 = l < a.L ? PH_FC2 : PH_HEAD;
-        c.tr_item = (tr && l == a.L / 2) ? tr + 300 : nullptr;
-#pragma unroll 1
-        for (int ph = ph0; ph <= ph1; ph++) {
-#pragma unroll 1
-            for (int i = 0; i < pg.n_items[ph]; i++) {
-                const PsItem it = pg.items[pg.first[ph] + i];
-                gemm_item<NG>(c, ph, l, t, it, gi, ctid);
-                gi += it.nst;
-            }
-            if (ph == PH_QKV) {
-                if (c.tr_item && ctid == 0) c.tr_item[3] = timer_ns();
+    for (int l = 0; l < a.L; l++) {
+        const PsLayer &Ly = a.layers[l];
+        const unsigned ep = ep0 + (unsigned)l;
+        unsigned long long *trl = c.tr ? c.tr + 1 + l * 12 : nullptr;
+        // ---- x -> LN1 -> qkv
+        if (pg.n_tiles[PH_QKV] > 0) {
+            if (l == 0) { bar_consumers(); load_x<2>(c, nullptr, Ly.ln1_g, Ly.ln1_b, 1e-5f, t, ctid); }
+            else { wait_flags(c, FL_X, ep, ctid, 31); load_x<1>(c, a.x, Ly.ln1_g, Ly.ln1_b, 1e-5f, t, ctid); }
+            bar_consumers();
+            if (trl && l < 48) trl[0] = timer_ns();
+            gemm_phase<0>(c, pg, PH_QKV, l, t, gi, ctid, Ly.bqkv, false);
+        }
+        signal_flag(c, FL_QKV, ep, ctid);
+        if (trl && l < 48) trl[1] = timer_ns();
+        // ---- attention
+        {
+            bool any = false;
+            for (int r = 0; r < pg.n_attn; r++) any = any || ((pg.attn[r] & 15) < a.B);
+            if (any) {
+                wait_flags(c, FL_QKV, ep, ctid, 32);
+                if (trl && l < 48) trl[2] = timer_ns();
 #pragma unroll 1
                 for (int bt = 0; bt < n_batches; bt++) {
-                    attn_batch<NG>(c, pg, bt, l, t, gi, ctid);
-                    gi += attn_stage_count<NG>(a, pg, bt, t);
+                    attn_batch(c, pg, bt, l, t, gi, ctid);
+                    gi += attn_stage_count(a, pg, bt, t);
+                    bar_consumers();
                 }
             }
-            if (tr && ctid == 0 && l < 48) tr[1 + l * 5 + ph] = timer_ns();
         }
+        signal_flag(c, FL_ATT, ep, ctid);
+        if (trl && l < 48) trl[3] = timer_ns();
+        // ---- y -> proj + residual -> xb
+        if (pg.n_tiles[PH_PROJ] > 0) {
+            wait_flags(c, FL_ATT, ep, ctid, 33);
+            load_x<0>(c, a.y, nullptr, nullptr, 0.f, t, ctid);
+            bar_consumers();
+            if (trl && l < 48) trl[4] = timer_ns();
+            gemm_phase<1>(c, pg, PH_PROJ, l, t, gi, ctid, Ly.bproj, false);
+        }
+        signal_flag(c, FL_XB, ep, ctid);
+        if (trl && l < 48) trl[5] = timer_ns();
+        // ---- xb -> LN2 -> fc1 -> GELU -> fc2 partial
+        if (pg.n_tiles[PH_FC1] > 0) {
+            wait_flags(c, FL_XB, ep, ctid, 34);
+            load_x<1>(c, a.xb, Ly.ln2_g, Ly.ln2_b, 1e-5f, t, ctid);
+            bar_consumers();
+            if (trl && l < 48) trl[6] = timer_ns();
+            gemm_phase<2>(c, pg, PH_FC1, l, t, gi, ctid, Ly.b1, false);
+            bar_consumers();
+            if (trl && l < 48) trl[7] = timer_ns();
+            fc2_phase(c, pg, gi, ctid);
+        }
+        signal_flag(c, FL_P, ep, ctid);
+        if (trl && l < 48) trl[8] = timer_ns();
+        // ---- reduce-scatter of the fc2 partials + bias + residual -> x
+        wait_flags(c, FL_P, ep, ctid, 35);
+        if (trl && l < 48) trl[9] = timer_ns();
+        reduce_phase(c, pg, Ly.b2, ctid);
+        signal_flag(c, FL_X, ep + 1, ctid);
+        if (trl && l < 48) trl[10] = timer_ns();
+        if (c.dead()) break;
     }
-    if (tr && ctid == 0) tr[1 + 48 * 5] = timer_ns();
+    // ---- LN_f + head
+    if (pg.n_tiles[PH_HEAD] > 0 && !c.dead()) {
+        wait_flags(c, FL_X, ep0 + (unsigned)a.L, ctid, 36);
+        load_x<1>(c, a.x, a.lnf_g, a.lnf_b, 1e-5f, t, ctid);
+        bar_consumers();
+        c.stamp(1 + 48 * 12);
+        gemm_phase<3>(c, pg, PH_HEAD, a.L, t, gi, ctid, nullptr, true);
+    }
+    c.stamp(2 + 48 * 12);
 }
 
-// Re-tiles a row-major weight W[N][K] into ring stages: dst[tile][kstage][warp 4][n8 tile 8][lane 32][4 floats] with
-// lane (g = lane / 4, tq = lane % 4) holding W[tile*64 + 8 j + g][kstage*64 + 16 warp + 4 tq .. + 3].
-__global__ void pack_weight_kernel(const float *__restrict__ W, int N, int K, float4 *__restrict__ dst) {
-    const size_t total = (size_t)N * K / 4;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int lane = (int)(i & 31), j = (int)((i >> 5) & 7), w = (int)((i >> 8) & 3);
-        const size_t stage = i >> 10;
-        const int KSt = K / 64;
-        const int tile = (int)(stage / KSt), ks = (int)(stage % KSt);
+// Re-tiles the weights of one layer (or the head) into the ring stages of every CTA, in consumption order.
+// grid = (G, stages per CTA rounded up), block = 256: one block per (CTA, stage).
+// Unit w of a K-type stage = [u 2][lane 32][4 floats]: lane (g = lane / 4, tq = lane % 4) holds
+// W[16 tile + 8 u + g][256 kc + 16 w + 4 tq .. + 3]; of an fc2-type stage: W2[256 nb + 16 w + 8 u + g][16 tile + 4 tq .. + 3].
+struct PackArgs {
+    const PsProg *prog;
+    const float *w[3];           // qkv [3d][d], proj [d][d], fc1 [4d][d]  (or head [V][d] in slot 0)
+    const float *w2;             // fc2 [d][4d]
+    uint8_t *dst;                // packed layer (or head) base
+    int d, KC, NBn, head, Nrows[3];
+};
+__global__ void pack_stage_kernel(const PackArgs p) {
+    const PsProg &pg = p.prog[blockIdx.x];
+    const int s = blockIdx.y;
+    const int n_stages = p.head ? (int)pg.head_stages : (int)pg.layer_stages;
+    if (s >= n_stages) return;
+    // locate the stage (same walk as ps_stage_src)
+    int ph = 0, tile = 0, kc = 0, nb = 0, rem = s;
+    bool found = false;
+    const int ph0 = p.head ? PH_HEAD : PH_QKV, ph1 = p.head ? PH_HEAD : PH_FC1;
+    for (int q = ph0; q <= ph1 && !found; q++) {
+        const int nt = pg.n_tiles[q], n = nt * p.KC;
+        if (rem < n) {
+            const int per_pass = PS_PASS_TILES * p.KC, pass = rem / per_pass, r2 = rem % per_pass;
+            const int nt_pass = min(PS_PASS_TILES, nt - pass * PS_PASS_TILES);
+            ph = q; kc = r2 / nt_pass; tile = pg.tiles[pg.first[q] + pass * PS_PASS_TILES + r2 % nt_pass];
+            found = true;
+        } else rem -= n;
+    }
+    if (!found) {
+        const int f = pg.n_tiles[PH_FC1];
+        ph = -1; nb = rem / f; tile = pg.tiles[pg.first[PH_FC1] + rem % f];
+    }
+    float4 *dst = reinterpret_cast<float4 *>(p.dst + ((size_t)(p.head ? pg.head_off16 : pg.layer_off16)) * 16 + (size_t)s * PS_STAGE_BYTES);
+    for (int i = threadIdx.x; i < PS_STAGE_BYTES / 16; i += blockDim.x) {
+        const int lane = i & 31, u = (i >> 5) & 1, w = i >> 6;
         const int g = lane >> 2, tq = lane & 3;
-        dst[i] = *reinterpret_cast<const float4 *>(W + (size_t)(tile * 64 + 8 * j + g) * K + ks * 64 + 16 * w + 4 * tq);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ph >= 0) {
+            const int src = p.head ? 0 : ph;
+            const int n = 16 * tile + 8 * u + g, k = PS_KS * kc + 16 * w + 4 * tq;
+            if (n < p.Nrows[src] && k < p.d) v = *reinterpret_cast<const float4 *>(p.w[src] + (size_t)n * p.d + k);
+        } else {
+            const int n = PS_NB * nb + 16 * w + 8 * u + g, k = 16 * tile + 4 * tq;
+            if (n < p.d) v = *reinterpret_cast<const float4 *>(p.w2 + (size_t)n * 4 * p.d + k);
+        }
+        dst[i] = v;
     }
 }
 

@@ -15,13 +15,13 @@ struct PstepWeights {            // borrowed fp32 device pointers, reference nn.
     const Layer *layers;         // [n_layer] host array
 };
 
-// true when the model tiles for the persistent kernel (d % 64 == 0, head_dim 64, V % 64 == 0, block_size <= 1024)
+// true when the model tiles for the persistent kernel (head_dim 64, d <= 1536, V % 16 == 0, block_size <= 1024, plan fits)
 bool pstep_eligible(const wmar_gpt_config &cfg, int n_sms);
 // plans, allocates and packs (re-tiles the weights into ring stages; ~ one extra copy of the model in HBM)
 int pstep_create(const wmar_gpt_config &cfg, int n_sms, const PstepWeights &w, float *kcache, float *vcache, float *logits,
                  const int *d_step, const int64_t *d_seq, int seq_ld, PstepState **out);
 void pstep_destroy(PstepState *s);
-// clears the {value, flag} buffers; once per generation (the token-step counter, part of every flag, restarts at 0)
+// clears the epoch flags; once per generation (the token-step counter, part of every epoch, restarts at 0)
 int pstep_reset(PstepState *s, cudaStream_t stream);
 // enqueues one token step (graph-capturable)
 int pstep_enqueue(PstepState *s, int B, int *d_err, cudaStream_t stream);
