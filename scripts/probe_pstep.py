@@ -27,7 +27,12 @@ for mode in modes:
     eng = TamingGPTEngine(w, c["n_layer"], c["n_head"])
     torch.cuda.synchronize()
     print(f"[{mode}] create {time.time() - t0:.2f} s", flush=True)
-    ids = eng.sample(cond, steps, 1.0, 250, 0.92, None, greedy=True)
+    try:
+        ids = eng.sample(cond, steps, 1.0, 250, 0.92, None, greedy=True)
+    except Exception as ex:
+        if not os.environ.get("WMAR_PSTEP_DBG"):
+            raise
+        ids = torch.zeros(16, steps, dtype=torch.long)
     torch.cuda.synchronize()
     rc = _lib.lib().wmar_check_device_flag(_lib.current_stream())
     print(f"[{mode}] device flag rc={rc} {_lib.lib().wmar_last_error().decode() if rc else ''}", flush=True)
@@ -35,7 +40,12 @@ for mode in modes:
     best = 1e9
     for _ in range(3):
         e0.record()
-        ids = eng.sample(cond, steps, 1.0, 250, 0.92, None, greedy=True)
+        try:
+            ids = eng.sample(cond, steps, 1.0, 250, 0.92, None, greedy=True)
+        except Exception as ex:            # knock-out runs (WMAR_PSTEP_DBG) produce garbage logits: time them anyway
+            if not os.environ.get("WMAR_PSTEP_DBG"):
+                raise
+            print("   (ignored:", str(ex)[:80], ")")
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
@@ -45,7 +55,7 @@ for mode in modes:
     out[mode] = ids.cpu()
     if mode.startswith("pstep") and os.environ.get("WMAR_PSTEP_TRACE"):
         L = _lib.lib()
-        G, EV = 148, 640
+        G, EV, PER = 148, 1024, 20
         buf = (ctypes.c_ulonglong * (G * EV))()
         L.wmar_gpt_debug_pstep_trace.restype = ctypes.c_int
         L.wmar_gpt_debug_pstep_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
@@ -54,23 +64,28 @@ for mode in modes:
             tr = np.frombuffer(buf, dtype=np.uint64).reshape(G, EV)[:n].astype(np.int64)
             t0s = tr[:, 0].min()
             nl = c["n_layer"]
-            ev = (tr[:, 1:1 + nl * 12].reshape(n, nl, 12) - t0s).astype(np.float64) / 1e3
-            ev[tr[:, 1:1 + nl * 12].reshape(n, nl, 12) == 0] = np.nan
-            end = (tr[:, 578] - t0s) / 1e3
-            names = ["x loaded", "qkv done", "qkv flags seen", "attention done", "y loaded", "proj done", "xb loaded",
-                     "fc1 done", "fc2 done", "partials seen", "x reduced"]
+            raw = tr[:, 1:1 + nl * PER].reshape(n, nl, PER)
+            ev = (raw - t0s).astype(np.float64) / 1e3
+            ev[raw == 0] = np.nan
+            end = (tr[:, 2 + 48 * PER] - t0s) / 1e3
+            names = ["x flags", "x loaded", "qkv loop", "qkv stored", "qkv signal", "qkv flags", "attention", "att signal",
+                     "y flags", "y loaded", "proj loop", "proj stored", "xb signal", "xb flags", "xb loaded", "fc1", "fc2",
+                     "fc2 signal", "part flags", "reduced+signal"]
             print(f"[{mode}] last step: kernel span {np.nanmax(end):.1f} us; start skew {(tr[:, 0].max() - t0s) / 1e3:.1f} us; "
-                  f"head starts at {np.nanmedian((tr[:, 577] - t0s) / 1e3):.1f} us")
-            for l in (0, 1, nl // 2, nl - 1):
-                prev = ev[:, l - 1, 10] if l > 0 else np.zeros(n)
-                seg, last = [], prev
-                for k in range(11):
+                  f"head starts at {np.nanmedian((tr[:, 1 + 48 * PER] - t0s) / 1e3):.1f} us")
+            for l in (1, nl // 2):
+                prev = ev[:, l - 1, PER - 1]
+                last = prev
+                print(f"   layer {l}: (median over CTAs of the time since the CTA's previous event; max; CTAs that ran it)")
+                for k in range(PER):
                     cur = ev[:, l, k]
-                    seg.append(f"{names[k]} +{np.nanmedian(cur - last):5.2f} (max {np.nanmax(cur - last):5.2f})")
+                    dt = cur - last
+                    if np.isfinite(dt).any():
+                        print(f"      {names[k]:>15s} +{np.nanmedian(dt):6.2f}  max {np.nanmax(dt):6.2f}  n={int(np.isfinite(dt).sum()):3d}   "
+                              f"(abs median {np.nanmedian(cur - np.nanmin(prev)):6.2f})")
                     last = np.where(np.isnan(cur), last, cur)
-                print(f"   layer {l:2d}: " + " | ".join(seg))
-                print(f"            layer time {np.nanmedian(ev[:, l, 10] - prev):.2f} us (slowest CTA ends {np.nanmax(ev[:, l, 10]) - np.nanmin(prev):.2f} us after the fastest start)")
-            per_layer = np.diff(np.nanmedian(ev[:, :, 10], axis=0))
+                print(f"      layer time {np.nanmedian(ev[:, l, PER - 1] - prev):.2f} us")
+            per_layer = np.diff(np.nanmedian(ev[:, :, PER - 1], axis=0))
             print(f"   median layer period {np.median(per_layer):.2f} us (min {per_layer.min():.2f}, max {per_layer.max():.2f})")
             np.save(os.path.join("gpurun_out", f"pstep_trace_{mode}.npy"), tr)
     del eng

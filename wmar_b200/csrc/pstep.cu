@@ -32,7 +32,7 @@ static int env_int(const char *name, int dflt) {
 
 bool pstep_eligible(const wmar_gpt_config &c, int n_sms) {
     if (c.n_embd % 64 != 0 || c.n_embd / c.n_head != 64 || c.n_embd % c.n_head != 0 || c.vocab_size % 16 != 0) return false;
-    if (c.n_embd > PS_DMAX || c.block_size > 1024 || c.n_layer > 200 || n_sms < 8) return false;
+    if (c.n_embd > PS_DMAX || c.block_size > 1024 || c.n_layer > 200 || n_sms < 8 || n_sms > PS_RED_NQ * PS_RED_MAXC) return false;
     int dev = 0, max_smem = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
     if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
@@ -106,7 +106,9 @@ int pstep_create(const wmar_gpt_config &cfg, int n_sms, const PstepWeights &w, f
     a.tok_emb = w.tok_emb; a.pos_emb = w.pos_emb; a.lnf_g = w.lnf_g; a.lnf_b = w.lnf_b;
     a.d = d; a.H = cfg.n_head; a.V = V; a.L = L; a.T = cfg.block_size; a.B = 0; a.G = s->G; a.GP = GP;
     a.Kp = pl.Kp; a.KC = pl.KC; a.NBn = pl.NBn;
-    a.pf_dist = (unsigned)std::max(0, env_int("WMAR_PSTEP_PF_KB", 256)) * 1024u;
+    a.pf_dist = (unsigned)std::max(0, env_int("WMAR_PSTEP_PF_KB", 0)) * 1024u;
+    a.wait_hint_ns = (unsigned)std::max(0, env_int("WMAR_PSTEP_HINT_NS", 20000));
+    a.dbg = env_int("WMAR_PSTEP_DBG", 0);
     a.step = d_step; a.seq = d_seq; a.seq_ld = seq_ld;
     auto F32 = [&](size_t o) { return reinterpret_cast<float *>(s->pool + o); };
     a.x = F32(o_x); a.xb = F32(o_xb); a.y = F32(o_y); a.qkv = F32(o_qkv); a.part = F32(o_part);

@@ -53,7 +53,7 @@ constexpr int PS_SMEM_BYTES = PS_OFF_DEAD + 16;
 constexpr int PS_ATT_SCRATCH = 8192;            // per warp group: scores[1024], q/k/v[192], part[8][64], red[8]
 constexpr unsigned PS_SPIN_LIMIT = 1u << 23;    // flag polls (~100 ns apart)
 constexpr unsigned PS_MBAR_LIMIT = 1u << 16;    // try_wait suspends up to 20 us each
-constexpr int PS_TRACE_EV = 640;
+constexpr int PS_TRACE_EV = 1024;                // probe only: 1 + 48 layers x 20 events + head
 static_assert(PS_SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(4 * PS_ATT_SCRATCH <= PS_X_BYTES && PS_PASS_TILES * 16 * 1024 <= PS_X_BYTES, "scratch aliases X");
 
@@ -72,6 +72,8 @@ struct PsArgs {
     const float *tok_emb, *pos_emb, *lnf_g, *lnf_b;
     int d, H, V, L, T, B, G, GP, Kp, KC, NBn;
     unsigned pf_dist;            // L2 prefetch distance of the weight stream, bytes per CTA
+    unsigned wait_hint_ns;       // mbarrier.try_wait suspend-time hint (0 = plain try_wait)
+    int dbg;                     // probe only (WMAR_PSTEP_DBG): bit 0 = skip the MMAs, bit 1 = skip the flag waits (results are garbage)
     const int *step;
     const int64_t *seq; int seq_ld;
     float *x, *xb, *y, *qkv;     // plain fp32 activations [16][d], [16][d], [16][d], [16][3d]
@@ -85,8 +87,10 @@ struct PsArgs {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 8, %0;" ::"n"(PS_NT) : "memory"); }
-__device__ __forceinline__ void bar_group(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+// barrier.sync without .aligned: the threads of a warp need not arrive convergently (a lane may still be in a poll loop
+// or a trace stamp when its warp mates reach the barrier)
+__device__ __forceinline__ void bar_consumers() { __syncwarp(); asm volatile("barrier.sync 8, %0;" ::"n"(PS_NT) : "memory"); }
+__device__ __forceinline__ void bar_group(int group) { __syncwarp(); asm volatile("barrier.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -130,17 +134,33 @@ struct Ctx {
         }
         return false;
     }
+    __device__ __forceinline__ bool try_wait(uint32_t bar, uint32_t parity) const {
+        uint32_t ok;
+        if (a.wait_hint_ns != 0u)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar), "r"(parity), "r"(a.wait_hint_ns) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        return ok != 0;
+    }
     __device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity, int code) const {
-        if (mbar_try_wait(bar, parity)) return;
+        if (try_wait(bar, parity)) return;
         unsigned n = 0;
-        while (!mbar_try_wait(bar, parity)) {
+        while (!try_wait(bar, parity)) {
             ++n;
             if (dead()) return;
             if ((n & 15u) == 0u && *reinterpret_cast<volatile int *>(a.abort_flag) != 0) { *reinterpret_cast<volatile int *>(s_dead) = 1; return; }
-            if (n > PS_MBAR_LIMIT) { timeout(code); return; }
+            if (n > (a.wait_hint_ns != 0u ? PS_MBAR_LIMIT : (PS_MBAR_LIMIT << 8))) { timeout(code); return; }
         }
     }
-    __device__ __forceinline__ void stamp(int ev) const { if (tr) tr[ev] = timer_ns(); }
+    // probe only; tr is set for the whole of consumer warp 0, lane 0 stores, the warp reconverges
+    __device__ __forceinline__ void stamp(int ev) const {
+        if (tr) {
+            if ((threadIdx.x & 31) == 0) tr[ev] = timer_ns();
+            __syncwarp();
+        }
+    }
 };
 
 // Release: every consumer thread's global stores of this phase are ordered before the CTA's epoch flag.
@@ -154,7 +174,7 @@ __device__ __forceinline__ void signal_flag(const Ctx &c, int which, unsigned ep
 // Acquire: consumer warp 0 polls the G flags of exchange `which` until all carry `epoch` (flags only grow inside a
 // generation), then the whole consumer side synchronises.  Returns with the data of all CTAs visible to ld.global.cg.
 __device__ __forceinline__ void wait_flags(const Ctx &c, int which, unsigned epoch, int ctid, int code) {
-    if (ctid < 32) {
+    if (ctid < 32 && !(c.a.dbg & 2)) {
         const unsigned *f = c.a.flags + which * c.a.GP;
         unsigned spins = 0;
         while (true) {
@@ -272,7 +292,7 @@ __device__ __forceinline__ void unit_mma(float (&acc)[2][4], const XFrag &x, con
 // EPI 0: + bias -> qkv (global)   1: + bias + residual -> xb (global)   2: + bias, GELU -> gelu slice (shared)   3: -> logits
 template <int EPI>
 __device__ __forceinline__ void gemm_phase(const Ctx &c, const PsProg &pg, int ph, int l, int t, uint32_t &gi, int ctid,
-                                           const float *bias, bool reload_ln) {
+                                           const float *bias, bool reload_ln, int trace_ev) {
     const PsArgs &a = c.a;
     const int lane = ctid & 31, cw = ctid >> 5, g = lane >> 2, tq = lane & 3;
     const int nt = pg.n_tiles[ph], ldx = a.Kp + PS_XPAD;
@@ -305,7 +325,8 @@ __device__ __forceinline__ void gemm_phase(const Ctx &c, const PsProg &pg, int p
                 if (i < np) {
                     const uint32_t gs = gi + (uint32_t)(kc * np + i), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
                     c.mbar_wait_b(full0 + slot * 8, parity, 14);
-                    unit_mma(acc[i], xf, c.smem + slot * PS_STAGE_BYTES + cw * 1024, lane);
+                    __syncwarp();          // mma.sync.aligned needs the warp converged after the per-lane wait loop
+                    if (!(a.dbg & 1)) unit_mma(acc[i], xf, c.smem + slot * PS_STAGE_BYTES + cw * 1024, lane);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty0 + slot * 8);
                 }
@@ -314,6 +335,7 @@ __device__ __forceinline__ void gemm_phase(const Ctx &c, const PsProg &pg, int p
         gi += (uint32_t)(a.KC * np);
         // cross-warp reduction in warp order; the scratch aliases X
         bar_consumers();
+        if (trace_ev >= 0) c.stamp(trace_ev);
 #pragma unroll
         for (int i = 0; i < PS_PASS_TILES; i++) {
             if (i < np) {
@@ -329,20 +351,10 @@ __device__ __forceinline__ void gemm_phase(const Ctx &c, const PsProg &pg, int p
         if (ctid < np * 64) {
             const int i = ctid >> 6, m = (ctid >> 2) & 15, n4 = (ctid & 3) * 4;
             const int tile = pg.tiles[pg.first[ph] + t0 + i], n = tile * 16 + n4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int w = 0; w < PS_NW; w++) {
-                const float4 p = *reinterpret_cast<const float4 *>(red + ((i * PS_NW + w) * 16 + m) * 16 + n4);
-                v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-            }
-            if (bias != nullptr) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + n));
-                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            }
-            if (EPI == 0) {
-                *reinterpret_cast<float4 *>(a.qkv + (size_t)m * 3 * a.d + n) = v;
-            } else if (EPI == 1) {
-                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            // global operands of the epilogue first: their latency overlaps the shared-memory reduction
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(bias + n));
+            if (EPI == 1) {
                 if (l == 0) {                 // layer 0: the residual is the embedding itself (mingpt.py:186-200)
                     if (m < a.B) {
                         long long id = a.seq[(size_t)m * a.seq_ld + t];
@@ -354,6 +366,17 @@ __device__ __forceinline__ void gemm_phase(const Ctx &c, const PsProg &pg, int p
                 } else {
                     r4 = ld_cg4(a.x + (size_t)m * a.d + n);
                 }
+            }
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < PS_NW; w++) {
+                const float4 p = *reinterpret_cast<const float4 *>(red + ((i * PS_NW + w) * 16 + m) * 16 + n4);
+                v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+            }
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (EPI == 0) {
+                *reinterpret_cast<float4 *>(a.qkv + (size_t)m * 3 * a.d + n) = v;
+            } else if (EPI == 1) {
                 v.x = r4.x + v.x; v.y = r4.y + v.y; v.z = r4.z + v.z; v.w = r4.w + v.w;
                 *reinterpret_cast<float4 *>(a.xb + (size_t)m * a.d + n) = v;
             } else if (EPI == 2) {
@@ -364,6 +387,7 @@ __device__ __forceinline__ void gemm_phase(const Ctx &c, const PsProg &pg, int p
                 if (m < a.B) *reinterpret_cast<float4 *>(a.logits + (size_t)m * a.V + n) = v;
             }
         }
+        if (trace_ev >= 0) c.stamp(trace_ev + 1);
     }
 }
 
@@ -389,7 +413,8 @@ __device__ __forceinline__ void fc2_phase(const Ctx &c, const PsProg &pg, uint32
             make_xfrag(xf, *reinterpret_cast<const float4 *>(xp), *reinterpret_cast<const float4 *>(xp + 8 * PS_HLD));
             const uint32_t gs = gi + (uint32_t)(nb * f + j), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
             c.mbar_wait_b(full0 + slot * 8, parity, 21);
-            unit_mma(acc, xf, c.smem + slot * PS_STAGE_BYTES + cw * 1024, lane);
+            __syncwarp();
+            if (!(a.dbg & 1)) unit_mma(acc, xf, c.smem + slot * PS_STAGE_BYTES + cw * 1024, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + slot * 8);
         }
@@ -405,41 +430,47 @@ __device__ __forceinline__ void fc2_phase(const Ctx &c, const PsProg &pg, uint32
     gi += (uint32_t)(a.NBn * f);
 }
 
-// x[slice] = xb[slice] + b2 + sum over CTAs (in CTA order) of their fc2 partials: the reduce-scatter half of fc2.
+// x[slice] = xb[slice] + b2 + sum over CTAs (fixed order) of their fc2 partials: the reduce-scatter half of fc2.
+// thread = (element e, group q): group q sums the partials of CTAs q, q + NQ, ... (all its loads in flight at once),
+// the groups are then added in q order through shared memory.
+constexpr int PS_RED_NQ = 12, PS_RED_PER = PS_NT / PS_RED_NQ, PS_RED_MAXC = 16;   // up to 12 x 16 = 192 CTAs
 __device__ __forceinline__ void reduce_phase(const Ctx &c, const PsProg &pg, const float *b2, int ctid) {
     const PsArgs &a = c.a;
     const int n = pg.red_hi - pg.red_lo;             // float4 elements of the flattened [16][d]
     float4 *scr = reinterpret_cast<float4 *>(c.smem + PS_OFF_X);
-    // thread = (element e, group q): group q sums the partials of CTAs q, q + NQ, ... ; groups are added in q order
-    int NQ = PS_NT / max(n, 1);
-    if (NQ > 8) NQ = 8;
-    if (NQ < 1) NQ = 1;
-    for (int e0 = 0; e0 < n; e0 += PS_NT / NQ) {
-        const int per = PS_NT / NQ;
-        const int e = e0 + ctid % per, q = ctid / per;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < n && q < NQ) {
-            const size_t idx = (size_t)(pg.red_lo + e) * 4;
+    for (int e0 = 0; e0 < n; e0 += PS_RED_PER) {
+        const int e = e0 + ctid % PS_RED_PER, q = ctid / PS_RED_PER;
+        const bool mine = e < n && q < PS_RED_NQ;
+        const size_t idx = (size_t)(pg.red_lo + (mine ? e : 0)) * 4;
+        float4 xb4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = xb4;
+        if (mine && q == 0) {
+            xb4 = ld_cg4(a.xb + idx);
+            b4 = __ldg(reinterpret_cast<const float4 *>(b2 + (int)(idx % (size_t)a.d)));
+        }
+        if (mine) {
             // CTAs without fc1 tiles never write their partial: it stays zero from create time
-#pragma unroll 4
-            for (int cc = q; cc < a.G; cc += NQ) {
-                const float4 p = ld_cg4(a.part + (size_t)cc * 16 * a.d + idx);
-                s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+            float4 p[PS_RED_MAXC];
+#pragma unroll
+            for (int k = 0; k < PS_RED_MAXC; k++) {
+                const int cc = q + k * PS_RED_NQ;
+                p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cc < a.G) p[k] = ld_cg4(a.part + (size_t)cc * 16 * a.d + idx);
             }
-            scr[q * per + (e - e0)] = s;
+            float4 s = p[0];
+#pragma unroll
+            for (int k = 1; k < PS_RED_MAXC; k++) { s.x += p[k].x; s.y += p[k].y; s.z += p[k].z; s.w += p[k].w; }
+            scr[q * PS_RED_PER + (e - e0)] = s;
         }
         bar_consumers();
-        if (e < n && q == 0) {
-            const size_t idx = (size_t)(pg.red_lo + e) * 4;
-            const int col = (int)(idx % (size_t)a.d);
-            float4 v = ld_cg4(a.xb + idx);
-            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(b2 + col));
+        if (mine && q == 0) {
             float4 sum = scr[e - e0];
-            for (int qq = 1; qq < NQ; qq++) {
-                const float4 p = scr[qq * per + (e - e0)];
-                sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+#pragma unroll
+            for (int qq = 1; qq < PS_RED_NQ; qq++) {
+                const float4 pp = scr[qq * PS_RED_PER + (e - e0)];
+                sum.x += pp.x; sum.y += pp.y; sum.z += pp.z; sum.w += pp.w;
             }
-            v.x += sum.x + b4.x; v.y += sum.y + b4.y; v.z += sum.z + b4.z; v.w += sum.w + b4.w;
+            float4 v;
+            v.x = xb4.x + (sum.x + b4.x); v.y = xb4.y + (sum.y + b4.y); v.z = xb4.z + (sum.z + b4.z); v.w = xb4.w + (sum.w + b4.w);
             *reinterpret_cast<float4 *>(a.x + idx) = v;
         }
         bar_consumers();
@@ -494,6 +525,7 @@ __device__ __forceinline__ void attn_batch(const Ctx &c, const PsProg &pg, int b
     for (int st = 0; st < nK; st++) {
         const uint32_t gs = gi + (uint32_t)(st * nact + ai), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
         c.mbar_wait_b(full0 + slot * 8, parity, 17);
+        __syncwarp();
         const uint8_t *base = c.smem + slot * PS_STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -544,6 +576,7 @@ __device__ __forceinline__ void attn_batch(const Ctx &c, const PsProg &pg, int b
     for (int st = 0; st < nK; st++) {
         const uint32_t gs = gi + (uint32_t)((nK + st) * nact + ai), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
         c.mbar_wait_b(full0 + slot * 8, parity, 18);
+        __syncwarp();
         const uint8_t *base = c.smem + slot * PS_STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -673,70 +706,78 @@ __global__ void __launch_bounds__(PS_THREADS, 1) pstep_kernel(const __grid_const
 
     // ================================================ consumers ================================================
     const int ctid = tid - 32;
-    c.tr = (a.trace && ctid == 0) ? a.trace + (size_t)cta * PS_TRACE_EV : nullptr;
+    c.tr = (a.trace && ctid < 32) ? a.trace + (size_t)cta * PS_TRACE_EV : nullptr;
     c.stamp(0);
     uint32_t gi = 0;
+    // trace events of a layer (probe only): 0 x flags seen, 1 x loaded, 2 qkv loop done, 3 qkv stored, 4 qkv signalled,
+    // 5 qkv flags seen, 6 attention done, 7 attention signalled, 8 y flags seen, 9 y loaded, 10 proj loop done,
+    // 11 proj stored, 12 xb signalled, 13 xb flags seen, 14 xb loaded, 15 fc1 done, 16 fc2 done, 17 fc2 signalled,
+    // 18 partial flags seen, 19 x reduced (+ signalled)
 #pragma unroll 1
     for (int l = 0; l < a.L; l++) {
         const PsLayer &Ly = a.layers[l];
         const unsigned ep = ep0 + (unsigned)l;
-        unsigned long long *trl = c.tr ? c.tr + 1 + l * 12 : nullptr;
+        const int tb = (l < 48) ? 1 + l * 20 : 1000;      // trace slot base of this layer (layers >= 48 share a spill slot)
         // ---- x -> LN1 -> qkv
         if (pg.n_tiles[PH_QKV] > 0) {
-            if (l == 0) { bar_consumers(); load_x<2>(c, nullptr, Ly.ln1_g, Ly.ln1_b, 1e-5f, t, ctid); }
-            else { wait_flags(c, FL_X, ep, ctid, 31); load_x<1>(c, a.x, Ly.ln1_g, Ly.ln1_b, 1e-5f, t, ctid); }
+            if (l == 0) { bar_consumers(); c.stamp(tb + 0); load_x<2>(c, nullptr, Ly.ln1_g, Ly.ln1_b, 1e-5f, t, ctid); }
+            else { wait_flags(c, FL_X, ep, ctid, 31); c.stamp(tb + 0); load_x<1>(c, a.x, Ly.ln1_g, Ly.ln1_b, 1e-5f, t, ctid); }
             bar_consumers();
-            if (trl && l < 48) trl[0] = timer_ns();
-            gemm_phase<0>(c, pg, PH_QKV, l, t, gi, ctid, Ly.bqkv, false);
+            c.stamp(tb + 1);
+            gemm_phase<0>(c, pg, PH_QKV, l, t, gi, ctid, Ly.bqkv, false, tb + 2);
         }
         signal_flag(c, FL_QKV, ep, ctid);
-        if (trl && l < 48) trl[1] = timer_ns();
+        c.stamp(tb + 4);
         // ---- attention
         {
             bool any = false;
             for (int r = 0; r < pg.n_attn; r++) any = any || ((pg.attn[r] & 15) < a.B);
             if (any) {
                 wait_flags(c, FL_QKV, ep, ctid, 32);
-                if (trl && l < 48) trl[2] = timer_ns();
+                c.stamp(tb + 5);
 #pragma unroll 1
                 for (int bt = 0; bt < n_batches; bt++) {
                     attn_batch(c, pg, bt, l, t, gi, ctid);
                     gi += attn_stage_count(a, pg, bt, t);
                     bar_consumers();
                 }
+                c.stamp(tb + 6);
             }
         }
         signal_flag(c, FL_ATT, ep, ctid);
-        if (trl && l < 48) trl[3] = timer_ns();
+        c.stamp(tb + 7);
         // ---- y -> proj + residual -> xb
         if (pg.n_tiles[PH_PROJ] > 0) {
             wait_flags(c, FL_ATT, ep, ctid, 33);
+            c.stamp(tb + 8);
             load_x<0>(c, a.y, nullptr, nullptr, 0.f, t, ctid);
             bar_consumers();
-            if (trl && l < 48) trl[4] = timer_ns();
-            gemm_phase<1>(c, pg, PH_PROJ, l, t, gi, ctid, Ly.bproj, false);
+            c.stamp(tb + 9);
+            gemm_phase<1>(c, pg, PH_PROJ, l, t, gi, ctid, Ly.bproj, false, tb + 10);
         }
         signal_flag(c, FL_XB, ep, ctid);
-        if (trl && l < 48) trl[5] = timer_ns();
+        c.stamp(tb + 12);
         // ---- xb -> LN2 -> fc1 -> GELU -> fc2 partial
         if (pg.n_tiles[PH_FC1] > 0) {
             wait_flags(c, FL_XB, ep, ctid, 34);
+            c.stamp(tb + 13);
             load_x<1>(c, a.xb, Ly.ln2_g, Ly.ln2_b, 1e-5f, t, ctid);
             bar_consumers();
-            if (trl && l < 48) trl[6] = timer_ns();
-            gemm_phase<2>(c, pg, PH_FC1, l, t, gi, ctid, Ly.b1, false);
+            c.stamp(tb + 14);
+            gemm_phase<2>(c, pg, PH_FC1, l, t, gi, ctid, Ly.b1, false, -1);
             bar_consumers();
-            if (trl && l < 48) trl[7] = timer_ns();
+            c.stamp(tb + 15);
             fc2_phase(c, pg, gi, ctid);
+            c.stamp(tb + 16);
         }
         signal_flag(c, FL_P, ep, ctid);
-        if (trl && l < 48) trl[8] = timer_ns();
+        c.stamp(tb + 17);
         // ---- reduce-scatter of the fc2 partials + bias + residual -> x
         wait_flags(c, FL_P, ep, ctid, 35);
-        if (trl && l < 48) trl[9] = timer_ns();
+        c.stamp(tb + 18);
         reduce_phase(c, pg, Ly.b2, ctid);
         signal_flag(c, FL_X, ep + 1, ctid);
-        if (trl && l < 48) trl[10] = timer_ns();
+        c.stamp(tb + 19);
         if (c.dead()) break;
     }
     // ---- LN_f + head
@@ -744,10 +785,10 @@ __global__ void __launch_bounds__(PS_THREADS, 1) pstep_kernel(const __grid_const
         wait_flags(c, FL_X, ep0 + (unsigned)a.L, ctid, 36);
         load_x<1>(c, a.x, a.lnf_g, a.lnf_b, 1e-5f, t, ctid);
         bar_consumers();
-        c.stamp(1 + 48 * 12);
-        gemm_phase<3>(c, pg, PH_HEAD, a.L, t, gi, ctid, nullptr, true);
+        c.stamp(1 + 48 * 20);
+        gemm_phase<3>(c, pg, PH_HEAD, a.L, t, gi, ctid, nullptr, true, -1);
     }
-    c.stamp(2 + 48 * 12);
+    c.stamp(2 + 48 * 20);
 }
 
 // Re-tiles the weights of one layer (or the head) into the ring stages of every CTA, in consumption order.
