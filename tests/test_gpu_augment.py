@@ -85,3 +85,49 @@ def test_round_trip_evaluation_on_device():
     # reference definition of l0 on one image (metrics.py:34)
     c, o = log["wm"]["flip-h"][1][1][0], codes[0]
     assert abs(float(m["flip-h"][1][1]["l0"][0]) - (o != c).sum().item() / o.shape[0]) < 1e-12
+
+
+def test_evaluation_log_values_match_the_reference():
+    """Value-level check of row f1: wmar_b200.evaluate.fill_batch_log + compute_metrics on the GPU (CUDA augmentations,
+    device detector) against tests/golden/evallog.npz = the REFERENCE's fill_batch_log (generate.py:111-164) +
+    compute_metric (metrics.py:25-45) + its own augmentation classes + GentimeWatermark.detect, run on the CPU over the
+    same toy tokenizer (helpers.ToyTokenizerModel).  Codes and l0 bit-exact; PSNR to 1e-9 wherever the 8-bit images of
+    the two sides are identical, else within 0.05 dB (blur / resize taps differ in the last float bit, which can move
+    one of 3072 8-bit pixels); p-values to 1e-9 relative."""
+    import os
+    from helpers import G, ToyTokenizerModel
+    from wmar_b200 import augmentations as A
+    from wmar_b200.evaluate import compute_metrics, fill_batch_log
+    from wmar_b200.watermarking import GentimeWatermark, SeedStrategy, SplitStrategy
+    g = np.load(os.path.join(G, "evallog.npz"))
+    model = ToyTokenizerModel("cuda")
+    V = 64
+    vq = {"alive_ids": torch.from_numpy(g["alive"]), "dead_ids": torch.from_numpy(g["dead"])}
+    wm = GentimeWatermark(vq, V, SeedStrategy.LINEAR, SplitStrategy.RANDOM_STRATIFIED, 1, 2.0, 0.25, device="cuda")
+    codes = torch.from_numpy(g["codes"]).cuda()
+    augs = [("gaussian-blur", lambda x, k: A.GaussianBlur()(x, k), [0, 3, 7]),
+            ("brightness", lambda x, b: A.Brightness()(x, b), [1, 1.5, 2.5]),
+            ("flip-h", lambda x, do: A.HorizontalFlip()(x) if do else x, [0, 1]),
+            ("upperleft-crop", lambda x, f: A.UpperLeftCropWithResizeBack()(x, f), [1.0, 0.8, 0.5])]
+    log = fill_batch_log({}, "wm", model, codes, {"max_roundtrips": 2, "augmentations": augs})
+    m = compute_metrics(log, "wm", wm)
+    n_checked = 0
+    for transform, entries in log["wm"].items():
+        for j, (param, c, imgs, _) in enumerate(entries):
+            assert float(param) == float(g[f"{transform}/{j}/param"])
+            want_codes = g[f"{transform}/{j}/codes"]
+            same_codes = np.array_equal(c.cpu().numpy(), want_codes)
+            got = m[transform][j][1]
+            if same_codes:
+                np.testing.assert_array_equal(got["l0"].cpu().numpy(), g[f"{transform}/{j}/l0"])
+                np.testing.assert_allclose(got["pvalue"].cpu().numpy(), g[f"{transform}/{j}/pvalue"], rtol=1e-9)
+                n_checked += 1
+            else:   # a block mean within float rounding of two colours: at most one code of the batch may differ
+                assert (c.cpu().numpy() != want_codes).sum() <= 1, (transform, j)
+            want_psnr, got_psnr = g[f"{transform}/{j}/psnr"], got["psnr"].cpu().numpy()
+            for b in range(len(want_psnr)):
+                if np.isinf(want_psnr[b]):
+                    assert np.isinf(got_psnr[b]), (transform, j, b)
+                else:
+                    assert abs(got_psnr[b] - want_psnr[b]) <= 0.05, (transform, j, b, got_psnr[b], want_psnr[b])
+    assert n_checked >= 12

@@ -174,3 +174,24 @@ def test_sampler_philox_distribution():
     freq = torch.bincount(out.cpu(), minlength=V)[:4].double() / B
     want = torch.softmax(logits[0, :4].double(), 0)
     assert torch.allclose(freq, want, atol=0.03), (freq, want)
+
+
+def test_clustering_split_on_device_matches_reference_golden():
+    """GentimeWatermark(FIXED, CLUSTERING): the one-row device table carries exactly the reference's greenlist
+    (tests/golden/clustering.npz), the logit processor adds delta on those ids only, and linear seeding is refused like
+    in the reference (gentime_watermark.py:177)."""
+    from wmar_b200.watermarking import GentimeWatermark, SeedStrategy, SplitStrategy
+    g = np.load(os.path.join(G, "clustering.npz"))
+    V = g["emb"].shape[0]
+    vq = {"alive_ids": torch.from_numpy(g["alive"]), "dead_ids": torch.from_numpy(g["dead"]),
+          "embedding": torch.from_numpy(g["emb"])}
+    wm = GentimeWatermark(vq, V, SeedStrategy.FIXED, SplitStrategy.CLUSTERING, 0, 2.0, 0.5, device="cuda")
+    assert str(wm) == "fixed-clustering-h=0-d=2.0-g=0.50"
+    assert sorted(wm.greenlist_ids_for_sum(0).cpu().tolist()) == sorted(g["green"].tolist())
+    logits = torch.zeros(2, V, device="cuda")
+    out = wm._process_logits(torch.zeros(2, 3, dtype=torch.long, device="cuda"), logits)
+    want = torch.zeros(V)
+    want[torch.from_numpy(g["green"])] = 2.0
+    assert torch.equal(out[0].cpu(), want) and torch.equal(out[1].cpu(), want)
+    with pytest.raises(AssertionError):
+        GentimeWatermark(vq, V, SeedStrategy.LINEAR, SplitStrategy.CLUSTERING, 1, 2.0, 0.5, device="cuda")

@@ -219,3 +219,73 @@ def test_chameleon_alive_ids_asset_is_the_reference_key():
     assert sorted(set(range(8192)) - set(alive)) == [0, 1, 2, 3]
     src = open(os.path.join(here, "wmar_b200", "models", "chameleon_wrapper.py")).read()
     assert "init_alivecodes" in src and "torch.arange(IMAGE_TOKEN_LO" not in src
+
+
+def test_clustering_split_matches_the_reference_golden():
+    """CLUSTERING split (gentime_watermark.py:175-216): the host routine reproduces the greenlist the reference's own
+    GentimeWatermark built from the same codebook (tests/golden/clustering.npz, oracle/gen_golden_clustering.py), id for
+    id and in the same order; the bitmask row it becomes on the device has exactly those bits."""
+    from wmar_b200.watermarking.clustering import clustering_greenlist_ids, ids_to_bitmask_row
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clustering.npz"))
+    green = clustering_greenlist_ids(torch.from_numpy(g["emb"]), g["alive"], g["dead"])
+    np.testing.assert_array_equal(np.asarray(green, dtype=np.int64), g["green"])
+    V = g["emb"].shape[0]
+    row = ids_to_bitmask_row(green, V)
+    bits = np.unpackbits(row.view(np.uint8), bitorder="little")[:V]
+    assert sorted(np.nonzero(bits)[0].tolist()) == sorted(g["green"].tolist())
+
+
+def test_precompute_imagenet_codes_host_logic(tmp_path):
+    """The bulk tokeniser (precompute_imagenet_codes.py equivalent): selection with the reference's numpy calls under
+    seed 1, the reference's file names, batching through images_to_codes -- with a stand-in model on the CPU."""
+    from PIL import Image
+    from wmar_b200 import precompute_imagenet_codes as pc
+    root = tmp_path / "imagenet"
+    wnids = ["n01440764", "n01443537", "n15075141"]
+    (root / "train").mkdir(parents=True)
+    (root / "labels.txt").write_text("".join(f"{w},name{i}\n" for i, w in enumerate(wnids)))
+    rng = np.random.default_rng(0)
+    for w in wnids:
+        (root / "train" / w).mkdir()
+        for k in range(5):
+            arr = rng.integers(0, 255, size=(40 + 3 * k, 48, 3), dtype=np.uint8)
+            Image.fromarray(arr).save(root / "train" / w / f"{w}_{k}.JPEG")
+    (tmp_path / "idx.json").write_text(json.dumps({"0": [wnids[0], "a"], "7": [wnids[1], "b"], "999": [wnids[2], "c"]}))
+
+    class StandIn:
+        device = "cpu"
+        calls = []
+
+        def images_to_codes(self, x):
+            assert x.shape[1:] == (3, 32, 32) and float(x.min()) >= -1 and float(x.max()) <= 1
+            self.calls.append(x.shape[0])
+            return (x.flatten(1)[:, :16] * 100).long()
+
+    labels = pc.load_labels(str(root))
+    assert labels == wnids
+    np.random.seed(1)
+    want = {}
+    for w in wnids:                                   # literal restatement of precompute_imagenet_codes.py:74-82
+        cls_paths = [os.path.join(str(root), "train", w, p) for p in os.listdir(os.path.join(str(root), "train", w))]
+        want[w] = np.random.choice(cls_paths, size=3, replace=False)
+        np.random.shuffle(want[w])
+    np.random.seed(1)
+    got = pc.select_paths(str(root), labels, {w: 3 for w in wnids})
+    assert all(list(got[w]) == list(want[w]) for w in wnids)
+
+    m = StandIn()
+    np.random.seed(1)
+    torch.manual_seed(1)
+    out = tmp_path / "out"
+    # monkeypatched counts: 3 per class instead of 50
+    orig = pc.counts_per_label
+    pc.counts_per_label = lambda labels, size, split=None: {w: 3 for w in labels}
+    try:
+        n = pc.run(m, str(root), str(out), 32, batch_size=2, classes={0, 999}, max_per_class=None,
+                   class_index_path=str(tmp_path / "idx.json"), log=lambda s: None)
+    finally:
+        pc.counts_per_label = orig
+    assert n == 6 and m.calls == [2, 1, 2, 1]
+    assert sorted(os.listdir(out / "codes")) == [f"{c}:{k:04}.npy" for c in (0, 999) for k in range(3)]
+    assert sorted(os.listdir(out / "images")) == [f"{c}:{k:04}.png" for c in (0, 999) for k in range(3)]
+    assert np.load(out / "codes" / "0:0000.npy").shape == (16,)

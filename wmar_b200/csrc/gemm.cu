@@ -80,7 +80,10 @@ int launch_skinny_gemm(int pro, int epi, const GemmArgs &a, cudaStream_t stream)
 
 int pick_splits(int N, int K, int n_sms) {
     const int tiles = N / GEMM_NT;
-    const int target = 2 * n_sms - 16;  // about one full wave at two CTAs per SM
+    // about one full wave at two CTAs per SM; WMAR_GEMM_WAVE=1: one CTA per SM, so that the NEXT kernel's CTAs fit
+    // beside this kernel's (2 x 96 KB of shared memory, 2 x 32 K registers) and stream their first weights early
+    static const int wave = []() { const char *e = getenv("WMAR_GEMM_WAVE"); return e ? atoi(e) : 2; }();
+    const int target = wave == 1 ? n_sms - 8 : 2 * n_sms - 16;
     int best = 1;
     for (int s = 1; s <= 64; s++) {
         if (K % (s * GEMM_KI) != 0 || K / (s * GEMM_KI) < GEMM_WARPS) continue;

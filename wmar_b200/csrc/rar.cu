@@ -15,11 +15,18 @@
 //     head:  (scale, shift) = Linear(SiLU(c_i)) ; logits = (LN_noaffine(x)(1+scale)+shift) Wlm^T + b  rar.py:131-134
 //     pass i >= 1 samples image token i-1:  u + (c - u) * cfg -> +delta on green(ids) -> /T -> softmax -> multinomial
 // KV cache: fp32 [layer][row16][head][seq+2][hd], one contiguous stream per (layer,row,head).
+//
+// adaLN hoisting: c_i depends only on (class, pass index), never on the tokens, so all modulation vectors of a
+// generation are computed BEFORE the token loop by one M-large GEMM per layer over the (B + 1) distinct condition rows
+// x (steps + 1) passes (rar.py:180,131-134,377), and a pass only gathers its 16 x 6d slice per layer (491 KB at XL)
+// instead of streaming the 6 d^2 adaLN weights of every layer (1.27 of 3.80 GB per pass at XL).  WMAR_RAR_HOIST=0 keeps
+// the per-pass GEMMs on their forked graph branch (round 1).
 #include <algorithm>
 #include <vector>
 
 #include "gemm.cuh"
 #include "sample.cuh"
+#include "conv_igemm.cuh"   // the 128 x 64 tile 3xTF32 GEMM, used for the hoisted adaLN tables
 
 using namespace wmar;
 
@@ -73,12 +80,61 @@ struct wmar_rar {
     size_t ws_bytes, ws_side_bytes;
     unsigned *counters_side;
     int launches_per_pass;
+    // hoisted adaLN tables: ada_in [Mpad][d] = SiLU(c) of row m = pass * (B + 1) + r' (r' < B: cond row, r' == B: the
+    // none-cond row); modtab [L][Mpad][6d], hmodtab [Mpad][2d]
+    bool hoist;
+    int m_pad;
+    float *ada_in, *modtab, *hmodtab;
 };
 
 namespace {
 
 __global__ void rar_init_kernel(int *pos) { *pos = 0; }
 __global__ void rar_advance_kernel(int *pos) { *pos += 1; }
+
+// Rows of the hoisted adaLN GEMM: m = pass * (B + 1) + r', SiLU(emb[cond row] + timesteps_embeddings[pass]) (rar.py:377,180);
+// rows beyond (steps + 1) * (B + 1) are zero padding up to a multiple of the GEMM's 128-row tile.
+__global__ void __launch_bounds__(256) rar_ada_input_kernel(const RarCall *cp, int codebook, int n_classes,
+                                                            const float *__restrict__ emb, const float *__restrict__ ts_embed,
+                                                            int d, float *__restrict__ ada_in) {
+    const int m = blockIdx.x, B = cp->B, R1 = B + 1;
+    const int pass = m / R1, r = m - pass * R1;
+    const bool valid = pass <= cp->steps;
+    long long cond_row = codebook + 1 + n_classes;
+    if (valid && r < B) {
+        long long cls = cp->cond[r];
+        if (cls < 0 || cls >= n_classes) cls = 0;
+        cond_row = codebook + 1 + cls;
+    }
+    for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            const float4 e = *reinterpret_cast<const float4 *>(emb + (size_t)cond_row * d + c);
+            const float4 ts = *reinterpret_cast<const float4 *>(ts_embed + (size_t)pass * d + c);
+            float cc[4] = {e.x + ts.x, e.y + ts.y, e.z + ts.z, e.w + ts.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) cc[k] = cc[k] / (1.0f + expf(-cc[k]));  // SiLU, same expression as rar_embed_kernel
+            o = make_float4(cc[0], cc[1], cc[2], cc[3]);
+        }
+        *reinterpret_cast<float4 *>(ada_in + (size_t)m * d + c) = o;
+    }
+}
+
+// This pass's modulation vectors: mod[l][r][6d] <- modtab[l][pass * (B + 1) + r'][6d] for the 2B rows (r' = r for the cond
+// rows, B for every none-cond row), and hmod[r][2d] likewise.  grid = (L + 1, 16).
+__global__ void __launch_bounds__(256) rar_mod_gather_kernel(const RarCall *cp, const int *pos, int seq, int m_pad, int d,
+                                                             int n_layer, const float *__restrict__ modtab,
+                                                             const float *__restrict__ hmodtab, float *__restrict__ mod,
+                                                             float *__restrict__ hmod) {
+    const int l = blockIdx.x, r = blockIdx.y, i = *pos, B = cp->B;
+    if (i > seq || r >= 2 * B) return;
+    const size_t m = (size_t)i * (B + 1) + (r < B ? r : B);
+    const int n = (l < n_layer ? 6 : 2) * d;
+    const float *src = l < n_layer ? modtab + ((size_t)l * m_pad + m) * n : hmodtab + m * n;
+    float *dst = l < n_layer ? mod + ((size_t)l * 16 + r) * n : hmod + (size_t)r * n;
+    for (int c = threadIdx.x * 4; c < n; c += blockDim.x * 4)
+        *reinterpret_cast<float4 *>(dst + c) = *reinterpret_cast<const float4 *>(src + c);
+}
 
 // x and SiLU(c) of pass i = *pos for the 16 rows (rows >= 2B zero), plus LN (mean, M2) partials of x per 64-col tile.
 __global__ void __launch_bounds__(256) rar_embed_kernel(const RarCall *cp, const int *pos, const int64_t *ids, int seq,
@@ -323,8 +379,9 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
                                         g->stats);
     WMAR_LAUNCH_CHECK();
     launches++;
-    // ---- forked branch: all adaLN modulations of this pass (they read SiLU(c) only) ----
-    const bool capturing = side != nullptr;
+    // ---- all adaLN modulations of this pass: gathered from the hoisted tables, or (WMAR_RAR_HOIST=0) computed by the
+    // per-pass GEMMs on a forked branch (they read SiLU(c) only) ----
+    const bool capturing = side != nullptr && !g->hoist;
     cudaStream_t ms = capturing ? side : s;
     const size_t mod_ld = (size_t)16 * 6 * d;
     if (capturing) {
@@ -336,17 +393,23 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
     WMAR_REQUIRE(5 * c.n_layer + 2 < 1024, "too many GEMM launches per pass for the hand-off flag");
     unsigned salt = 0;
     auto ll = [&](GemmArgs &q) { if (ll_on) { q.ll_epoch = g->pos; q.ll_salt = ++salt; } };
-    for (int l = 0; l < c.n_layer; l++) {
-        const RarLayer &L = g->layers[l];
-        GemmArgs m{};
-        m.ws = g->ws_side; m.counters = g->counters_side;
-        m.X = g->csilu; m.ldx = d; m.W = L.wada; m.bias = L.bada; m.Y = g->mod + l * mod_ld; m.ldy = 6 * d; m.N = 6 * d; m.K = d;
-        m.splits = g->s_ada;
-        ll(m);
-        if ((rc = launch_skinny_gemm(PRO_NONE, EPI_STORE, m, ms))) return rc;
-        if (capturing) WMAR_CUDA_CHECK(cudaEventRecord(g_layer_event(l), side));
-    }
-    {
+    if (g->hoist) {
+        rar_mod_gather_kernel<<<dim3((unsigned)c.n_layer + 1, 16), 256, 0, s>>>(g->d_call, g->pos, c.image_seq_len, g->m_pad, d,
+                                                                             c.n_layer, g->modtab, g->hmodtab, g->mod, g->hmod);
+        WMAR_LAUNCH_CHECK();
+        launches++;
+    } else {
+        for (int l = 0; l < c.n_layer; l++) {
+            const RarLayer &L = g->layers[l];
+            GemmArgs m{};
+            m.ws = g->ws_side; m.counters = g->counters_side;
+            m.X = g->csilu; m.ldx = d; m.W = L.wada; m.bias = L.bada; m.Y = g->mod + l * mod_ld; m.ldy = 6 * d; m.N = 6 * d; m.K = d;
+            m.splits = g->s_ada;
+            ll(m);
+            if ((rc = launch_skinny_gemm(PRO_NONE, EPI_STORE, m, ms))) return rc;
+            if (capturing) WMAR_CUDA_CHECK(cudaEventRecord(g_layer_event(l), side));
+            launches++;
+        }
         GemmArgs hm{};
         hm.ws = g->ws_side; hm.counters = g->counters_side;
         hm.X = g->csilu; hm.ldx = d; hm.W = g->whada; hm.bias = g->bhada; hm.Y = g->hmod; hm.ldy = 2 * d; hm.N = 2 * d; hm.K = d;
@@ -354,6 +417,7 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
         ll(hm);
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_STORE, hm, ms))) return rc;
         if (capturing) WMAR_CUDA_CHECK(cudaEventRecord(g_layer_event(c.n_layer), side));
+        launches++;
     }
     for (int l = 0; l < c.n_layer; l++) {
         const RarLayer &L = g->layers[l];
@@ -401,7 +465,7 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
         o.stats_out = g->stats;
         ll(o);
         if ((rc = launch_skinny_gemm(PRO_NONE, EPI_GATE_RESID, o, s))) return rc;
-        launches += 6;
+        launches += 5;
     }
     if (capturing) WMAR_CUDA_CHECK(cudaStreamWaitEvent(s, g_layer_event(c.n_layer), 0));   // joins the forked branch
     GemmArgs lm{};
@@ -419,7 +483,7 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
     WMAR_LAUNCH_CHECK();
     rar_advance_kernel<<<1, 1, 0, s>>>(g->pos);
     WMAR_LAUNCH_CHECK();
-    launches += 5;
+    launches += 4;
     g->launches_per_pass = launches;
     return WMAR_OK;
 }
@@ -432,6 +496,7 @@ int wmar_rar_create(const wmar_rar_config *cfg, const void *const *d_weights, in
     WMAR_REQUIRE(cfg != nullptr && d_weights != nullptr && out != nullptr, "NULL argument");
     WMAR_REQUIRE(cfg->hidden % 64 == 0 && cfg->hidden % cfg->n_head == 0, "hidden must be a multiple of 64 and of n_head");
     WMAR_REQUIRE(cfg->mlp % 64 == 0 && cfg->codebook_size % 64 == 0, "mlp % 64 == 0 and codebook % 64 == 0 required");
+    WMAR_REQUIRE((2 * cfg->hidden) % CV_BN == 0 && cfg->hidden % CV_BK == 0, "hidden must tile the adaLN table GEMM");
     const int hd = cfg->hidden / cfg->n_head;
     WMAR_REQUIRE(hd % 4 == 0 && hd <= 128, "head_dim must be a multiple of 4 and <= 128");
     WMAR_REQUIRE(cfg->image_seq_len >= 1 && cfg->image_seq_len + 2 <= 1280, "image_seq_len out of range");
@@ -514,6 +579,19 @@ int wmar_rar_create(const wmar_rar_config *cfg, const void *const *d_weights, in
     WMAR_CUDA_CHECK(cudaMemset(g->stats, 0, sizeof(float2) * (d / 64) * 16));
     g->graph = nullptr; g->exec = nullptr; g->graph_smem = 0; g->graph_B = 0;
     g->launches_per_pass = 6 * cfg->n_layer + 6;
+    {
+        const char *e = getenv("WMAR_RAR_HOIST");
+        g->hoist = !(e && e[0] == '0');
+        g->ada_in = g->modtab = g->hmodtab = nullptr;
+        g->m_pad = ((cfg->image_seq_len + 1) * (cfg->max_batch + 1) + CV_BM - 1) / CV_BM * CV_BM;
+        if (g->hoist) {
+            WMAR_CUDA_CHECK(cudaMalloc(&g->ada_in, sizeof(float) * (size_t)g->m_pad * d));
+            WMAR_CUDA_CHECK(cudaMalloc(&g->modtab, sizeof(float) * (size_t)cfg->n_layer * g->m_pad * 6 * d));
+            WMAR_CUDA_CHECK(cudaMalloc(&g->hmodtab, sizeof(float) * (size_t)g->m_pad * 2 * d));
+            const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
+            WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+    }
     *out = g;
     return WMAR_OK;
 }
@@ -523,6 +601,7 @@ void wmar_rar_destroy(wmar_rar *g) {
     cudaDeviceSynchronize();
     rar_free_graph(g);
     cudaFree(g->ws_side); cudaFree(g->counters_side);
+    cudaFree(g->ada_in); cudaFree(g->modtab); cudaFree(g->hmodtab);
     cudaFree(g->x); cudaFree(g->csilu); cudaFree(g->mod); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->hbuf);
     cudaFree(g->hmod); cudaFree(g->logits); cudaFree(g->guided); cudaFree(g->kcache); cudaFree(g->vcache); cudaFree(g->ws);
     cudaFree(g->stats); cudaFree(g->counters); cudaFree(g->ids); cudaFree(g->pos); cudaFree(g->d_call);
@@ -580,6 +659,27 @@ int wmar_rar_sample(wmar_rar *g, const wmar_wm_params *wm, const wmar_sample_par
     WMAR_CUDA_CHECK(cudaMemsetAsync(g->ws_side, 0, g->ws_side_bytes, s));
     rar_init_kernel<<<1, 1, 0, s>>>(g->pos);
     WMAR_LAUNCH_CHECK();
+    if (g->hoist) {
+        // every modulation vector of this generation, before the token loop: one M-large 3xTF32 GEMM per layer over the
+        // (steps + 1) x (B + 1) distinct (pass, condition) rows
+        const int d = g->d;
+        const int M = ((int)steps + 1) * ((int)B + 1), Mp = (M + CV_BM - 1) / CV_BM * CV_BM;
+        WMAR_REQUIRE(Mp <= g->m_pad, "adaLN table too small");
+        rar_ada_input_kernel<<<Mp, 256, 0, s>>>(g->d_call, g->cfg.codebook_size, g->cfg.n_classes, g->emb, g->ts_embed, d, g->ada_in);
+        WMAR_LAUNCH_CHECK();
+        const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
+        for (int l = 0; l <= g->cfg.n_layer; l++) {
+            const bool head = l == g->cfg.n_layer;
+            ConvArgs a{};
+            a.in = g->ada_in; a.w = head ? g->whada : g->layers[l].wada; a.bias = head ? g->bhada : g->layers[l].bada;
+            a.resid = nullptr;
+            a.out = head ? g->hmodtab : g->modtab + (size_t)l * g->m_pad * 6 * d;
+            a.B = 1; a.Hs = 1; a.Ws = Mp; a.Cin = d; a.Ho = 1; a.Wo = Mp; a.Cout = (head ? 2 : 6) * d; a.Cout_pad = a.Cout;
+            a.ks = 1; a.stride = 1; a.pad = 0; a.up = 0; a.out_scale = 1.f;
+            conv_igemm_kernel<1><<<dim3((unsigned)(Mp / CV_BM), (unsigned)(a.Cout / CV_BN)), CV_THREADS, smem, s>>>(a);
+            WMAR_LAUNCH_CHECK();
+        }
+    }
     for (int64_t i = 0; i <= steps; i++) {  // pass 0 = cls token (fills the cache only), pass i >= 1 samples token i-1
         WMAR_CUDA_CHECK(cudaGraphLaunch(g->exec, s));
         g_launches.fetch_add((uint64_t)g->launches_per_pass);
@@ -590,13 +690,21 @@ int wmar_rar_sample(wmar_rar *g, const wmar_wm_params *wm, const wmar_sample_par
 double wmar_rar_algorithmic_bytes(const wmar_rar *g, int64_t B, int64_t steps) {
     if (!g) return 0.0;
     const double d = g->d, V = g->cfg.codebook_size, L = g->cfg.n_layer, mlp = g->cfg.mlp;
-    // dense parameters streamed once per pass: per block 4 d^2 + 2 d mlp + 6 d^2 (adaLN) + biases/norms,
-    // head 2 d^2 + V d
-    const double P = L * (10.0 * d * d + 2.0 * d * mlp + 9.0 * d + mlp + 6.0 * d + 4.0 * d + 4.0 * (d / g->cfg.n_head)) +
-                     2.0 * d * d + 2.0 * d + V * d + V;
+    // dense parameters streamed once per pass: per block 4 d^2 + 2 d mlp (+ 6 d^2 adaLN when not hoisted)
+    // + biases / norms, head V d (+ 2 d^2 adaLN when not hoisted)
+    const double ada = g->hoist ? 0.0 : 1.0;
+    const double P = L * ((4.0 + 6.0 * ada) * d * d + 2.0 * d * mlp + 9.0 * d + mlp + 6.0 * d * ada + 4.0 * d + 4.0 * (d / g->cfg.n_head)) +
+                     ada * (2.0 * d * d + 2.0 * d) + V * d + V;
     double kv = 0.0;  // per row: i+1 keys read at pass i, one appended
     for (int64_t i = 0; i <= steps; i++) kv += 2.0 * L * d * (double)(i + 1) + 2.0 * L * d;
-    return 4.0 * (P * (double)(steps + 1) + kv * 2.0 * (double)B);
+    double hoisted = 0.0;
+    if (g->hoist) {
+        // once per generation: the adaLN weights read once, the tables written once; per pass: 2B rows x (6 d L + 2 d) read
+        const double rows = (double)(steps + 1) * (double)(B + 1);
+        hoisted = (6.0 * d * d + 6.0 * d) * L + 2.0 * d * d + 2.0 * d + rows * (6.0 * d * L + 2.0 * d) +
+                  (double)(steps + 1) * 2.0 * (double)B * (6.0 * d * L + 2.0 * d);
+    }
+    return 4.0 * (P * (double)(steps + 1) + kv * 2.0 * (double)B + hoisted);
 }
 
 }  // extern "C"

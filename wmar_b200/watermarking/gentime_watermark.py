@@ -69,8 +69,18 @@ class GentimeWatermark:
         self.greenlist_size = int(self.vocab_size * self.gamma)
         self.spatial_dim = spatial_dim
         if self.split_strategy is SplitStrategy.CLUSTERING:
-            raise NotImplementedError("CLUSTERING split (TSNE+KMeans, fixed seeding only) is not built yet "
-                                      "(SURVEY.md section 8 row f3)")
+            # gentime_watermark.py:175-177: one fixed greenlist from t-SNE + KMeans of the alive codebook vectors (host,
+            # once per watermarker) -> the single row of the bitmask table
+            assert self.seed_strategy is SeedStrategy.FIXED, "Clustering only with fixed seeding"
+            from .clustering import clustering_greenlist_ids, ids_to_bitmask_row
+            emb = vq["embedding"] if isinstance(vq, dict) else vq.embedding.weight
+            ids = clustering_greenlist_ids(emb, self.alive_ids.cpu(), self.dead_ids.cpu())
+            self.n_rows = 1
+            self.table = torch.from_numpy(ids_to_bitmask_row(ids, self.vocab_size)).view(1, -1).to(self.device)
+            self._params = _lib.WmParams(self.table.data_ptr(), self.n_rows, self.vocab_size,
+                                         _SEED_CODE[self.seed_strategy], self.context_size, self.spatial_dim, self.delta,
+                                         self.gamma)
+            return
         if self.seed_strategy is SeedStrategy.SPATIAL and self.context_size not in (1, 3):
             raise AssertionError("Spatial seeding only implemented for context size in [1,3]")
 
