@@ -191,3 +191,23 @@ def test_full_size_taming_vs_oracle():
     print(f"full-size parity: worst |dlogit|/range = {worst:.2e}; argmax equal on {decided} decided (row, step) pairs "
           f"(smallest decided gap {min_gap:.3e}), {undecided} pairs inside the error bound")
     assert decided >= 3 * R * 8 // 4
+
+
+@pytest.mark.parametrize("step_mode", ["graph", "pstep"])
+def test_thousand_generations_never_match_a_stale_handoff_word(step_mode):
+    """Stress of the fence-free {value, flag} split-K hand-off (gemm.cuh) and of the epoch flags of the persistent kernel:
+    1000 generations back to back on one engine (the flag is (step + 1) * 1024 + launch index, the workspace is cleared by
+    a cudaMemsetAsync at the start of every generation, so a stale word of generation g - 1 must never satisfy a poll of
+    generation g).  Alternating batch sizes and conditionings; every result must equal the first run of its input."""
+    os.environ["WMAR_STEP"] = step_mode
+    try:
+        g, w, eng, (V, block, L, H, d, steps, B) = _engine("tiny")
+    finally:
+        os.environ.pop("WMAR_STEP", None)
+    wm = make_wm("taming")
+    conds = [torch.from_numpy(g["tiny/cond"]).long(), (torch.arange(16) * 61 + 5) % 1000, torch.tensor([7, 7, 7])]
+    want = [eng.sample(c, steps, 1.0, 250, 0.92, wm, greedy=True).clone() for c in conds]
+    for it in range(1000):
+        k = it % 3
+        got = eng.sample(conds[k], steps, 1.0, 250, 0.92, wm, greedy=True)
+        assert torch.equal(got, want[k]), (it, k)

@@ -80,6 +80,7 @@ struct wmar_gpt {
     unsigned *hflag;   // [n_layer][4d/128] arrival counters
     // persistent step kernel (pstep.cuh): the default path, one launch per token step instead of 5 per layer
     PstepState *pstep;
+    int *ticket;       // arrival counter of gpt_tail_kernel (self-resetting)
 };
 
 namespace {
@@ -269,6 +270,71 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) gpt_sample_kernel(const Cal
 }
 
 __global__ void advance_step_kernel(int *step) { *step += 1; }
+
+// The whole tail of a token step in ONE launch (default; WMAR_TAIL=0 keeps sample / advance / embed as three kernels):
+// CTA b samples row b (watermark + warpers + multinomial, as gpt_sample_kernel), then embeds the sampled token for the
+// NEXT position (x[b] = tok_emb[id] + pos_emb[t + 1] and the LayerNorm partials, as embed_kernel) -- a row only needs
+// its own id -- and the last CTA to finish advances the step counter (ticket).  grid = 16: rows >= B are zeroed.
+__global__ void __launch_bounds__(SAMPLE_THREADS, 1) gpt_tail_kernel(const CallParams *cp, const float *__restrict__ logits,
+                                                                      int64_t *seq, int seq_ld, int *step, int *ticket, int *err,
+                                                                      const float *__restrict__ tok_emb,
+                                                                      const float *__restrict__ pos_emb, int d, int block_size,
+                                                                      float *__restrict__ x, float2 *__restrict__ stats) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int s_id;
+    const int b = blockIdx.x, t = *step;
+    const SampleArgs a = cp->sa;
+    const bool valid = b < cp->B;
+    if (valid) {
+        const float *row = logits + (size_t)b * a.V;
+        if (cp->out_logits != nullptr) {
+            float *dst = cp->out_logits + ((size_t)t * cp->B + b) * a.V;
+            for (int v = threadIdx.x; v < a.V; v += SAMPLE_THREADS) dst[v] = row[v];
+        }
+        const float *noise = cp->noise ? cp->noise + ((size_t)t * cp->B + b) * a.V : nullptr;
+        const int id = sample_row(a, row, seq + (size_t)b * seq_ld, (long long)t + 1, noise,
+                                  ((unsigned long long)t << 32) | (unsigned)b, err, smem_raw);
+        if (threadIdx.x == 0) {
+            seq[(size_t)b * seq_ld + t + 1] = id;
+            cp->out_codes[(size_t)b * cp->steps + t] = id;
+            s_id = id;
+        }
+    }
+    __syncthreads();
+    const int tn = t + 1;
+    if (tn < block_size) {       // after the last token there is no next position
+        long long id = valid ? s_id : 0;
+        if (id < 0 || id >= a.V) id = 0;
+        const int lane16 = threadIdx.x & 15;
+        for (int c0 = (threadIdx.x >> 4) * 64; c0 < d; c0 += (SAMPLE_THREADS >> 4) * 64) {
+            const int c = c0 + lane16 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const float4 e = *reinterpret_cast<const float4 *>(tok_emb + (size_t)id * d + c);
+                const float4 p = *reinterpret_cast<const float4 *>(pos_emb + (size_t)tn * d + c);
+                v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+            }
+            *reinterpret_cast<float4 *>(x + (size_t)b * d + c) = v;
+            float s = v.x + v.y + v.z + v.w;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * (1.0f / 64.0f);
+            const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+            float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            if (lane16 == 0) stats[(c0 / 64) * 16 + b] = make_float2(mean, q);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {   // every CTA has read `t`: the step may advance
+            *ticket = 0;
+            *step = t + 1;
+        }
+    }
+}
 
 int free_graph(wmar_gpt *g) {
     if (g->exec) cudaGraphExecDestroy(g->exec);
@@ -474,14 +540,22 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
     launches += 1;
     int *err = device_err_flag();
     WMAR_REQUIRE(err != nullptr, "cannot allocate the device error flag");
-    gpt_sample_kernel<<<B, SAMPLE_THREADS, sample_smem, s>>>(g->d_call, g->logits, g->seq, c.block_size + 1, g->step, err);
-    WMAR_LAUNCH_CHECK();
-    advance_step_kernel<<<1, 1, 0, s>>>(g->step);
-    WMAR_LAUNCH_CHECK();
-    embed_kernel<<<16, 256, 0, s>>>(g->d_call, g->seq, c.block_size + 1, g->step, g->tok_emb, g->pos_emb, d, c.block_size,
-                                    V, g->x, g->stats);
-    WMAR_LAUNCH_CHECK();
-    launches += 3;
+    static const bool one_tail = []() { const char *e = getenv("WMAR_TAIL"); return !(e && e[0] == '0'); }();
+    if (one_tail) {
+        gpt_tail_kernel<<<16, SAMPLE_THREADS, sample_smem, s>>>(g->d_call, g->logits, g->seq, c.block_size + 1, g->step, g->ticket, err,
+                                                               g->tok_emb, g->pos_emb, d, c.block_size, g->x, g->stats);
+        WMAR_LAUNCH_CHECK();
+        launches += 1;
+    } else {
+        gpt_sample_kernel<<<B, SAMPLE_THREADS, sample_smem, s>>>(g->d_call, g->logits, g->seq, c.block_size + 1, g->step, err);
+        WMAR_LAUNCH_CHECK();
+        advance_step_kernel<<<1, 1, 0, s>>>(g->step);
+        WMAR_LAUNCH_CHECK();
+        embed_kernel<<<16, 256, 0, s>>>(g->d_call, g->seq, c.block_size + 1, g->step, g->tok_emb, g->pos_emb, d, c.block_size,
+                                        V, g->x, g->stats);
+        WMAR_LAUNCH_CHECK();
+        launches += 3;
+    }
     g->launches_per_step = launches;
     return WMAR_OK;
 }
@@ -540,6 +614,8 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
     WMAR_CUDA_CHECK(cudaMalloc(&g->counters, sizeof(unsigned) * max_tiles));
     WMAR_CUDA_CHECK(cudaMalloc(&g->seq, sizeof(int64_t) * 16 * (cfg->block_size + 1)));
     WMAR_CUDA_CHECK(cudaMalloc(&g->step, sizeof(int)));
+    WMAR_CUDA_CHECK(cudaMalloc(&g->ticket, sizeof(int)));
+    WMAR_CUDA_CHECK(cudaMemset(g->ticket, 0, sizeof(int)));
     WMAR_CUDA_CHECK(cudaMalloc(&g->d_call, sizeof(CallParams)));
     WMAR_CUDA_CHECK(cudaMallocHost(&g->h_call, sizeof(CallParams)));
     WMAR_CUDA_CHECK(cudaEventCreateWithFlags(&g->call_done, cudaEventDisableTiming));
@@ -614,7 +690,7 @@ void wmar_gpt_destroy(wmar_gpt *g) {
     free_graph(g);
     cudaFree(g->x); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->hbuf); cudaFree(g->logits);
     cudaFree(g->kcache); cudaFree(g->vcache); cudaFree(g->ws); cudaFree(g->stats); cudaFree(g->counters);
-    cudaFree(g->seq); cudaFree(g->step); cudaFree(g->d_call); cudaFreeHost(g->h_call);
+    cudaFree(g->seq); cudaFree(g->step); cudaFree(g->ticket); cudaFree(g->d_call); cudaFreeHost(g->h_call);
     cudaFree(g->ws2); cudaFree(g->d_trace); cudaFree(g->hpart); cudaFree(g->hflag);
     pstep_destroy(g->pstep);
     cudaEventDestroy(g->call_done);
@@ -651,6 +727,7 @@ int wmar_gpt_sample(wmar_gpt *g, const wmar_wm_params *wm, const wmar_sample_par
     if (g->exec == nullptr || g->graph_smem != smem || g->graph_B != (int)B) {
         free_graph(g);
         WMAR_CUDA_CHECK(cudaFuncSetAttribute(gpt_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(gpt_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaStream_t cs;
         WMAR_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         WMAR_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));

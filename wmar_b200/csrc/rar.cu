@@ -206,14 +206,24 @@ __global__ void __launch_bounds__(RAR_ATT_THREADS) rar_attn_kernel(const float *
     __shared__ float red[8];
     // programmatic dependent launch: the proj GEMM may start (and request its first weights) while this kernel runs
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // qkv comes from the previous kernel
-    const int h = blockIdx.x, r = blockIdx.y, i = *pos;
-    if (i >= T) return;
+    const int h = blockIdx.x, r = blockIdx.y, i = *pos;   // the pass counter was advanced at the end of the previous pass
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float *q = qkv + (size_t)r * 3 * d + h * hd;
-    const float *kn = q + d, *vn = q + 2 * d;
     const size_t base = (((size_t)layer * 16 + r) * H + h) * (size_t)T * hd;
     float *K = kcache + base, *V = vcache + base;
+    // K and V rows of EARLIER passes are final: ask L2 for them before waiting for this pass's q,k,v, so that the loads
+    // after the wait are L2 hits (the HBM round trip overlaps the tail of the qkv GEMM, as in attn_decode_kernel)
+    if (i > 0 && i < T) {
+        const size_t bytes = (size_t)i * hd * sizeof(float);
+        const char *kp = reinterpret_cast<const char *>(K), *vp = reinterpret_cast<const char *>(V);
+        for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)RAR_ATT_THREADS * 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + off));
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // qkv comes from the previous kernel
+    if (i >= T) return;
+    const float *q = qkv + (size_t)r * 3 * d + h * hd;
+    const float *kn = q + d, *vn = q + 2 * d;
     if (warp < 2) {  // warp 0: q, warp 1: new k  (nn.LayerNorm(hd, eps 1e-6), rar.py:82-83,103)
         const float *src = warp == 0 ? q : kn;
         const float *g = warp == 0 ? qn_g : kn_g, *bb = warp == 0 ? qn_b : kn_b;
