@@ -129,6 +129,7 @@ def test_full_size_taming_properties(B):
             eng = TamingGPTEngine(w, c["n_layer"], c["n_head"])
         finally:
             os.environ.pop("WMAR_STEP", None)
+        print("full-size properties: mode", mode, flush=True)
         ids = eng.sample(cond, c["block_size"], 1.0, 250, 0.92, wm, greedy=True)
         again = eng.sample(cond, c["block_size"], 1.0, 250, 0.92, wm, greedy=True)
         assert torch.equal(ids, again), mode                      # deterministic

@@ -495,101 +495,120 @@ __device__ __forceinline__ void attn_batch(const Ctx &c, const PsProg &pg, int b
     const int tid128 = ctid & 127, sub = lane & 15, hf = lane >> 4;
     const uint32_t full0 = smem_u32(c.smem + PS_OFF_BARS), empty0 = full0 + PS_NS * 8;
     const int r = batch * 4 + group;
-    if (r >= pg.n_attn) return;
-    const int item = pg.attn[r], h = item >> 4, b = item & 15;
-    if (b >= a.B) return;                     // inactive row: y keeps its (finite) old contents, nobody reads the row
+    const int item = r < pg.n_attn ? pg.attn[r] : 0, h = item >> 4, b = item & 15;
+    // inactive groups (no item, or a row >= B whose y keeps its finite old contents) still take part in the ring
+    // protocol below: EVERY consumer warp waits for and releases EVERY stage, in ring order.  (If only the owning group
+    // touched a stage, a group could wait for ring index s while the previous fill of that slot, index s - 7 of another
+    // group, is still in flight; mbarrier.try_wait.parity only sees the phase bit and would pass on the wrong data.)
+    const bool mine = r < pg.n_attn && b < a.B;
     const int d = a.d;
     int nact = 0, ai = 0;
     for (int i = 0; i < 4; i++) {
         const int rr = batch * 4 + i;
         if (rr < pg.n_attn && (pg.attn[rr] & 15) < a.B) { if (i < group) ai++; nact++; }
     }
+    if (nact == 0) return;
     const int nK = (t + 63) >> 6;
     float *scr = reinterpret_cast<float *>(c.smem + PS_OFF_X + group * PS_ATT_SCRATCH);
     float *sc = scr, *qs = scr + 1024, *kn = scr + 1088, *vn = scr + 1152, *part = scr + 1216, *redv = scr + 1728;
     const size_t cbase = (((size_t)l * 16 + b) * a.H + h) * (size_t)a.T * 64;
 
     // 1. this step's q, k, v (written by the qkv tiles' owners); k, v are appended to the cache for later steps
-    if (tid128 < 48) {
-        const int which = tid128 >> 4, cq = tid128 & 15;
-        const float4 v4 = ld_cg4(a.qkv + (size_t)b * 3 * d + which * d + h * 64 + 4 * cq);
-        *reinterpret_cast<float4 *>(scr + 1024 + which * 64 + 4 * cq) = v4;
-        if (which == 1) *reinterpret_cast<float4 *>(a.kcache + cbase + (size_t)t * 64 + 4 * cq) = v4;
-        if (which == 2) *reinterpret_cast<float4 *>(a.vcache + cbase + (size_t)t * 64 + 4 * cq) = v4;
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mine) {
+        if (tid128 < 48) {
+            const int which = tid128 >> 4, cq = tid128 & 15;
+            const float4 v4 = ld_cg4(a.qkv + (size_t)b * 3 * d + which * d + h * 64 + 4 * cq);
+            *reinterpret_cast<float4 *>(scr + 1024 + which * 64 + 4 * cq) = v4;
+            if (which == 1) *reinterpret_cast<float4 *>(a.kcache + cbase + (size_t)t * 64 + 4 * cq) = v4;
+            if (which == 2) *reinterpret_cast<float4 *>(a.vcache + cbase + (size_t)t * 64 + 4 * cq) = v4;
+        }
+        bar_group(group);
+        q4 = *reinterpret_cast<const float4 *>(qs + 4 * sub);
     }
-    bar_group(group);
-    const float4 q4 = *reinterpret_cast<const float4 *>(qs + 4 * sub);
     const float scale = 0.125f;               // 1 / sqrt(64)
 
     // 2. scores: half-warp per key, 16 keys of every stage per warp
     for (int st = 0; st < nK; st++) {
-        const uint32_t gs = gi + (uint32_t)(st * nact + ai), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
-        c.mbar_wait_b(full0 + slot * 8, parity, 17);
-        __syncwarp();
-        const uint8_t *base = c.smem + slot * PS_STAGE_BYTES;
+        for (int j = 0; j < nact; j++) {
+            const uint32_t gs = gi + (uint32_t)(st * nact + j), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
+            c.mbar_wait_b(full0 + slot * 8, parity, 17);
+            __syncwarp();
+            if (mine && j == ai) {
+                const uint8_t *base = c.smem + slot * PS_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int jl = wg * 16 + i * 2 + hf, j = st * 64 + jl;
-            float s = 0.f;
-            if (j < t) {
-                const float4 k4 = *reinterpret_cast<const float4 *>(base + jl * 256 + sub * 16);
-                s = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+                for (int i = 0; i < 8; i++) {
+                    const int jl = wg * 16 + i * 2 + hf, jj = st * 64 + jl;
+                    float sv = 0.f;
+                    if (jj < t) {
+                        const float4 k4 = *reinterpret_cast<const float4 *>(base + jl * 256 + sub * 16);
+                        sv = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+                    }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                    if (sub == 0 && jj < t) sc[jj] = sv * scale;
+                }
             }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (sub == 0 && j < t) sc[j] = s * scale;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + slot * 8);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cnt(empty0 + slot * 8, 4);
     }
-    if (wg == 0) {                             // this step's own key
-        const float4 k4 = *reinterpret_cast<const float4 *>(kn + 4 * sub);
-        float s = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+    float inv = 0.f;
+    if (mine) {
+        if (wg == 0) {                             // this step's own key
+            const float4 k4 = *reinterpret_cast<const float4 *>(kn + 4 * sub);
+            float sv = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) sc[t] = s * scale;
-    }
-    bar_group(group);
+            for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+            if (lane == 0) sc[t] = sv * scale;
+        }
+        bar_group(group);
 
-    // 3. softmax over keys 0..t
-    const int nk = t + 1;
-    float mx = -INFINITY;
-    for (int j = tid128; j < nk; j += 128) mx = fmaxf(mx, sc[j]);
-    mx = warp_max(mx);
-    if (lane == 0) redv[wg] = mx;
-    bar_group(group);
-    mx = fmaxf(fmaxf(redv[0], redv[1]), fmaxf(redv[2], redv[3]));
-    float sum = 0.f;
-    for (int j = tid128; j < nk; j += 128) {
-        const float e = expf(sc[j] - mx);
-        sc[j] = e;
-        sum += e;
+        // 3. softmax over keys 0..t
+        const int nk = t + 1;
+        float mx = -INFINITY;
+        for (int j = tid128; j < nk; j += 128) mx = fmaxf(mx, sc[j]);
+        mx = warp_max(mx);
+        if (lane == 0) redv[wg] = mx;
+        bar_group(group);
+        mx = fmaxf(fmaxf(redv[0], redv[1]), fmaxf(redv[2], redv[3]));
+        float sum = 0.f;
+        for (int j = tid128; j < nk; j += 128) {
+            const float e = expf(sc[j] - mx);
+            sc[j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) redv[4 + wg] = sum;
+        bar_group(group);
+        sum = (redv[4] + redv[5]) + (redv[6] + redv[7]);
+        inv = 1.0f / sum;
     }
-    sum = warp_sum(sum);
-    if (lane == 0) redv[4 + wg] = sum;
-    bar_group(group);
-    sum = (redv[4] + redv[5]) + (redv[6] + redv[7]);
-    const float inv = 1.0f / sum;
 
     // 4. P.V
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int st = 0; st < nK; st++) {
-        const uint32_t gs = gi + (uint32_t)((nK + st) * nact + ai), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
-        c.mbar_wait_b(full0 + slot * 8, parity, 18);
-        __syncwarp();
-        const uint8_t *base = c.smem + slot * PS_STAGE_BYTES;
+        for (int j = 0; j < nact; j++) {
+            const uint32_t gs = gi + (uint32_t)((nK + st) * nact + j), slot = gs % PS_NS, parity = (gs / PS_NS) & 1u;
+            c.mbar_wait_b(full0 + slot * 8, parity, 18);
+            __syncwarp();
+            if (mine && j == ai) {
+                const uint8_t *base = c.smem + slot * PS_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int jl = wg * 16 + i * 2 + hf, j = st * 64 + jl;
-            if (j < t) {
-                const float4 v4 = *reinterpret_cast<const float4 *>(base + jl * 256 + sub * 16);
-                const float p = sc[j];
-                acc.x += p * v4.x; acc.y += p * v4.y; acc.z += p * v4.z; acc.w += p * v4.w;
+                for (int i = 0; i < 8; i++) {
+                    const int jl = wg * 16 + i * 2 + hf, jj = st * 64 + jl;
+                    if (jj < t) {
+                        const float4 v4 = *reinterpret_cast<const float4 *>(base + jl * 256 + sub * 16);
+                        const float p = sc[jj];
+                        acc.x += p * v4.x; acc.y += p * v4.y; acc.z += p * v4.z; acc.w += p * v4.w;
+                    }
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + slot * 8);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cnt(empty0 + slot * 8, 4);
     }
+    if (!mine) return;
     if (wg == 0 && hf == 0) {
         const float4 v4 = *reinterpret_cast<const float4 *>(vn + 4 * sub);
         const float p = sc[t];
