@@ -248,6 +248,131 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const float *q
     }
 }
 
+// Second form of the attention kernel: FOUR lanes per key (each lane 4 consecutive float4 of the 64-wide row), 64 lane
+// groups x 4 keys = all 256 cached keys of the Taming sequence requested in ONE sweep, before griddepcontrol.wait (K into
+// registers, V as an L2 prefetch), and two shuffle steps per score instead of four.  Opt-in (WMAR_ATTN4=1): slower here.
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_decode4_kernel(const float *qkv, int d, int H, int T, float *kcache,
+                                                                      float *vcache, int layer, const int *step,
+                                                                      float *__restrict__ y) {
+    constexpr int HD = 64, F4 = 4, KB = 4, GROUPS = ATT_THREADS / 4;
+    __shared__ float sc[1024];
+    __shared__ __align__(16) float part[GROUPS / 2][HD];
+    __shared__ float red[ATT_THREADS / 32];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int h = blockIdx.x, b = blockIdx.y, t = *step;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid >> 2, sub = tid & 3;
+    const float *q = qkv + (size_t)b * 3 * d + h * HD;
+    const float *kn = q + d, *vn = q + 2 * d;
+    const size_t base = (((size_t)layer * 16 + b) * H + h) * (size_t)T * HD;
+    float *K = kcache + base, *Vc = vcache + base;
+    const int nk = t + 1;
+    float4 k4[KB][F4];
+#pragma unroll
+    for (int u = 0; u < KB; u++) {
+        const int j = grp + u * GROUPS;
+#pragma unroll
+        for (int f = 0; f < F4; f++)
+            k4[u][f] = j < t ? *reinterpret_cast<const float4 *>(K + (size_t)j * HD + (sub * F4 + f) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (t > 0) {
+        const size_t bytes = (size_t)t * HD * sizeof(float);
+        const char *vp = reinterpret_cast<const char *>(Vc), *kp = reinterpret_cast<const char *>(K);
+        for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)ATT_THREADS * 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + off));
+            if (off >= (size_t)GROUPS * KB * HD * sizeof(float)) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + off));
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // qkv comes from the previous kernel
+    float4 q4[F4];
+#pragma unroll
+    for (int f = 0; f < F4; f++) q4[f] = __ldcg(reinterpret_cast<const float4 *>(q + (sub * F4 + f) * 4));
+    if (tid < 16) *reinterpret_cast<float4 *>(K + (size_t)t * HD + 4 * tid) = __ldcg(reinterpret_cast<const float4 *>(kn + 4 * tid));
+    else if (tid < 32) *reinterpret_cast<float4 *>(Vc + (size_t)t * HD + 4 * (tid - 16)) = __ldcg(reinterpret_cast<const float4 *>(vn + 4 * (tid - 16)));
+    const float scale = 1.0f / sqrtf((float)HD);
+    for (int jb = 0; jb < nk; jb += GROUPS * KB) {
+#pragma unroll
+        for (int u = 0; u < KB; u++) {
+            const int j = jb + grp + u * GROUPS;
+            float sd = 0.f;
+#pragma unroll
+            for (int f = 0; f < F4; f++) {
+                float4 kk;
+                if (j == t) kk = __ldcg(reinterpret_cast<const float4 *>(kn + (sub * F4 + f) * 4));   // this step's own key
+                else if (jb == 0) kk = k4[u][f];
+                else kk = j < t ? *reinterpret_cast<const float4 *>(K + (size_t)j * HD + (sub * F4 + f) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                sd += q4[f].x * kk.x + q4[f].y * kk.y + q4[f].z * kk.z + q4[f].w * kk.w;
+            }
+            sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+            sd += __shfl_xor_sync(0xffffffffu, sd, 2);
+            if (sub == 0 && j < nk) sc[j] = sd * scale;
+        }
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int j = tid; j < nk; j += ATT_THREADS) m = fmaxf(m, sc[j]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < ATT_THREADS / 32; w++) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < nk; j += ATT_THREADS) {
+        float e = expf(sc[j] - m);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < ATT_THREADS / 32; w++) sum += red[w];
+    const float inv = 1.0f / sum;
+    float4 acc[F4];
+#pragma unroll
+    for (int f = 0; f < F4; f++) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jb = 0; jb < nk; jb += GROUPS * KB) {
+        float4 v4[KB][F4];
+#pragma unroll
+        for (int u = 0; u < KB; u++) {
+            const int j = jb + grp + u * GROUPS;
+#pragma unroll
+            for (int f = 0; f < F4; f++) {
+                if (j == t) v4[u][f] = __ldcg(reinterpret_cast<const float4 *>(vn + (sub * F4 + f) * 4));
+                else v4[u][f] = j < t ? *reinterpret_cast<const float4 *>(Vc + (size_t)j * HD + (sub * F4 + f) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < KB; u++) {
+            const int j = jb + grp + u * GROUPS;
+            const float p = j < nk ? sc[j] * inv : 0.f;
+#pragma unroll
+            for (int f = 0; f < F4; f++) {
+                acc[f].x += p * v4[u][f].x; acc[f].y += p * v4[u][f].y; acc[f].z += p * v4[u][f].z; acc[f].w += p * v4[u][f].w;
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < F4; f++) {
+        acc[f].x += __shfl_xor_sync(0xffffffffu, acc[f].x, 4); acc[f].y += __shfl_xor_sync(0xffffffffu, acc[f].y, 4);
+        acc[f].z += __shfl_xor_sync(0xffffffffu, acc[f].z, 4); acc[f].w += __shfl_xor_sync(0xffffffffu, acc[f].w, 4);
+    }
+    if ((lane & 4) == 0) {
+#pragma unroll
+        for (int f = 0; f < F4; f++) *reinterpret_cast<float4 *>(&part[grp >> 1][(sub * F4 + f) * 4]) = acc[f];
+    }
+    __syncthreads();
+    if (tid < HD) {
+        float o = 0.f;
+#pragma unroll 8
+        for (int w = 0; w < GROUPS / 2; w++) o += part[w][tid];
+        y[(size_t)b * d + h * HD + tid] = o;
+    }
+}
+
 // lm_head epilogue: watermark + sampler for row b; writes the id into seq / out_codes and (optionally) the raw logits
 __global__ void __launch_bounds__(SAMPLE_THREADS, 1) gpt_sample_kernel(const CallParams *cp, const float *__restrict__ logits,
                                                                         int64_t *seq, int seq_ld, const int *step, int *err) {
@@ -503,8 +628,15 @@ int enqueue_step(wmar_gpt *g, int B, size_t sample_smem, cudaStream_t s) {
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_decode_kernel<64>, (const float *)g->qkv, d, H, c.block_size, g->kcache,
-                                               g->vcache, l, (const int *)g->step, g->y));
+            // measured on Taming C2: 2896 us / token with the 4-lane kernel vs 2742 with the 16-lane one (which also holds
+            // the first 128 V rows in registers before the wait) -> opt-in only; the RAR engine's twin is its default
+            static const bool attn4 = []() { const char *e = getenv("WMAR_ATTN4"); return e && e[0] == '1'; }();
+            if (attn4)
+                WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_decode4_kernel, (const float *)g->qkv, d, H, c.block_size, g->kcache,
+                                                   g->vcache, l, (const int *)g->step, g->y));
+            else
+                WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_decode_kernel<64>, (const float *)g->qkv, d, H, c.block_size, g->kcache,
+                                                   g->vcache, l, (const int *)g->step, g->y));
             g_launches.fetch_add(1);
         }
         // x += y Wproj^T + b

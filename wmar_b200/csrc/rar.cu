@@ -319,6 +319,156 @@ __global__ void __launch_bounds__(RAR_ATT_THREADS) rar_attn_kernel(const float *
     }
 }
 
+// Second form of the attention kernel (head_dim % 16 == 0: 32, 64, 80, 128): FOUR lanes per key, each lane owning F4
+// consecutive float4 of the key row, eight keys per warp instruction and KB keys per lane group in flight, so that all
+// (up to 256) cached keys of a pass are requested in ONE round trip -- and requested BEFORE griddepcontrol.wait: K rows of
+// earlier passes are final, they land in registers while the qkv GEMM is still running.  The kernel above needs a whole
+// warp (20 of 32 lanes busy at head_dim 80) and eight round trips per 512 keys.
+template <int F4>
+__global__ void __launch_bounds__(RAR_ATT_THREADS, 2) rar_attn4_kernel(const float *qkv, int d, int H, int T,
+                                                                    const float *__restrict__ qn_g, const float *__restrict__ qn_b,
+                                                                    const float *__restrict__ kn_g, const float *__restrict__ kn_b,
+                                                                    float *kcache, float *vcache,
+                                                                    int layer, const int *pos, float *__restrict__ y) {
+    constexpr int HD = 16 * F4, KB = F4 <= 4 ? 4 : 2, GROUPS = RAR_ATT_THREADS / 4;   // 64 lane groups x KB keys per sweep
+    __shared__ __align__(16) float sq[128];
+    __shared__ float sc[1280];
+    __shared__ __align__(16) float part[GROUPS / 2][HD];
+    __shared__ float red[8];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int h = blockIdx.x, r = blockIdx.y, i = *pos;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid >> 2, sub = tid & 3;
+    const size_t base = (((size_t)layer * 16 + r) * H + h) * (size_t)T * HD;
+    float *K = kcache + base, *V = vcache + base;
+    const int nprev = i < T ? i : 0;                   // cached keys 0 .. i-1 (this pass's own key comes after the wait)
+    float4 k4[KB][F4];
+#pragma unroll
+    for (int u = 0; u < KB; u++) {
+        const int j = grp + u * GROUPS;
+#pragma unroll
+        for (int f = 0; f < F4; f++)
+            k4[u][f] = j < nprev ? *reinterpret_cast<const float4 *>(K + (size_t)j * HD + (sub * F4 + f) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (nprev > 0) {   // V (and the K rows past the first sweep): L2 prefetch, read after the softmax
+        const size_t bytes = (size_t)nprev * HD * sizeof(float);
+        const char *vp = reinterpret_cast<const char *>(V), *kp = reinterpret_cast<const char *>(K);
+        for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)RAR_ATT_THREADS * 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + off));
+            if (off >= (size_t)GROUPS * KB * HD * sizeof(float)) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + off));
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // qkv comes from the previous kernel
+    if (i >= T) return;
+    const float *q = qkv + (size_t)r * 3 * d + h * HD;
+    const float *kn = q + d, *vn = q + 2 * d;
+    if (warp < 2) {  // warp 0: q, warp 1: new k  (nn.LayerNorm(hd, eps 1e-6), rar.py:82-83,103)
+        const float *src = warp == 0 ? q : kn;
+        const float *g = warp == 0 ? qn_g : kn_g, *bb = warp == 0 ? qn_b : kn_b;
+        float s = 0.f;
+        for (int c = lane; c < HD; c += 32) s += __ldcg(src + c);
+        s = warp_sum(s);
+        const float mean = s / (float)HD;
+        float v2 = 0.f;
+        for (int c = lane; c < HD; c += 32) { float dd = __ldcg(src + c) - mean; v2 += dd * dd; }
+        v2 = warp_sum(v2);
+        const float rstd = 1.0f / sqrtf(v2 / (float)HD + 1e-6f);
+        for (int c = lane; c < HD; c += 32) {
+            float o = (__ldcg(src + c) - mean) * rstd * g[c] + bb[c];
+            if (warp == 0) sq[c] = o;
+            else K[(size_t)i * HD + c] = o;
+        }
+    } else if (warp == 2) {
+        for (int c = lane; c < HD; c += 32) V[(size_t)i * HD + c] = __ldcg(vn + c);
+    }
+    __syncthreads();
+    const float scale = 1.0f / sqrtf((float)HD);
+    const int nk = i + 1;
+    float4 q4[F4];
+#pragma unroll
+    for (int f = 0; f < F4; f++) q4[f] = *reinterpret_cast<const float4 *>(sq + (sub * F4 + f) * 4);
+    for (int jb = 0; jb < nk; jb += GROUPS * KB) {      // block-uniform trip count
+#pragma unroll
+        for (int u = 0; u < KB; u++) {
+            const int j = jb + grp + u * GROUPS;
+            float sd = 0.f;
+#pragma unroll
+            for (int f = 0; f < F4; f++) {
+                float4 kk;
+                if (jb == 0 && j < nprev) kk = k4[u][f];
+                else kk = j < nk ? *reinterpret_cast<const float4 *>(K + (size_t)j * HD + (sub * F4 + f) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                sd += q4[f].x * kk.x + q4[f].y * kk.y + q4[f].z * kk.z + q4[f].w * kk.w;
+            }
+            sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+            sd += __shfl_xor_sync(0xffffffffu, sd, 2);
+            if (sub == 0 && j < nk) sc[j] = sd * scale;
+        }
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int j = tid; j < nk; j += RAR_ATT_THREADS) m = fmaxf(m, sc[j]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < nk; j += RAR_ATT_THREADS) {
+        float e = expf(sc[j] - m);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sum += red[w];
+    const float inv = 1.0f / sum;
+    float4 acc[F4];
+#pragma unroll
+    for (int f = 0; f < F4; f++) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jb = 0; jb < nk; jb += GROUPS * KB) {
+        float4 v4[KB][F4];
+#pragma unroll
+        for (int u = 0; u < KB; u++) {
+            const int j = jb + grp + u * GROUPS;
+#pragma unroll
+            for (int f = 0; f < F4; f++)
+                v4[u][f] = j < nk ? *reinterpret_cast<const float4 *>(V + (size_t)j * HD + (sub * F4 + f) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < KB; u++) {
+            const int j = jb + grp + u * GROUPS;
+            const float p = j < nk ? sc[j] * inv : 0.f;
+#pragma unroll
+            for (int f = 0; f < F4; f++) {
+                acc[f].x += p * v4[u][f].x; acc[f].y += p * v4[u][f].y; acc[f].z += p * v4[u][f].z; acc[f].w += p * v4[u][f].w;
+            }
+        }
+    }
+    // 64 lane groups hold partial outputs over disjoint key sets: pairs of groups first (shuffle across lanes 4 apart),
+    // then 32 partial rows through shared memory, summed in a fixed order
+#pragma unroll
+    for (int f = 0; f < F4; f++) {
+        acc[f].x += __shfl_xor_sync(0xffffffffu, acc[f].x, 4); acc[f].y += __shfl_xor_sync(0xffffffffu, acc[f].y, 4);
+        acc[f].z += __shfl_xor_sync(0xffffffffu, acc[f].z, 4); acc[f].w += __shfl_xor_sync(0xffffffffu, acc[f].w, 4);
+    }
+    if ((lane & 4) == 0) {
+#pragma unroll
+        for (int f = 0; f < F4; f++) *reinterpret_cast<float4 *>(&part[grp >> 1][(sub * F4 + f) * 4]) = acc[f];
+    }
+    __syncthreads();
+    if (tid < HD) {
+        float o = 0.f;
+#pragma unroll 8
+        for (int w = 0; w < GROUPS / 2; w++) o += part[w][tid];
+        y[(size_t)r * d + h * HD + tid] = o;
+    }
+}
+
 // guided = u + (c - u) * cfg (rar.py:441) for cond row b; a separate launch so that the sampler below may read the row
 // through the read-only path.
 __global__ void __launch_bounds__(256) rar_guide_kernel(const RarCall *cp, const float *__restrict__ logits,
@@ -450,9 +600,20 @@ int rar_enqueue_pass(wmar_rar *g, int B, size_t sample_smem, cudaStream_t s, cud
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rar_attn_kernel, (const float *)g->qkv, d, H, g->hd, g->T,
-                                               (const float *)L.qn_g, (const float *)L.qn_b, (const float *)L.kn_g, (const float *)L.kn_b,
-                                               g->kcache, g->vcache, l, (const int *)g->pos, g->y));
+            static const bool attn4 = []() { const char *e = getenv("WMAR_RAR_ATTN4"); return !(e && e[0] == '0'); }();
+#define WMAR_RAR_ATTN4(F4)                                                                                                      \
+    WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rar_attn4_kernel<F4>, (const float *)g->qkv, d, H, g->T, (const float *)L.qn_g,    \
+                                       (const float *)L.qn_b, (const float *)L.kn_g, (const float *)L.kn_b, g->kcache,         \
+                                       g->vcache, l, (const int *)g->pos, g->y))
+            if (attn4 && g->hd == 32) WMAR_RAR_ATTN4(2);
+            else if (attn4 && g->hd == 64) WMAR_RAR_ATTN4(4);
+            else if (attn4 && g->hd == 80) WMAR_RAR_ATTN4(5);
+            else if (attn4 && g->hd == 128) WMAR_RAR_ATTN4(8);
+            else
+                WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rar_attn_kernel, (const float *)g->qkv, d, H, g->hd, g->T,
+                                                   (const float *)L.qn_g, (const float *)L.qn_b, (const float *)L.kn_g, (const float *)L.kn_b,
+                                                   g->kcache, g->vcache, l, (const int *)g->pos, g->y));
+#undef WMAR_RAR_ATTN4
         }
         GemmArgs p{};
         p.ws = g->ws; p.counters = g->counters;

@@ -157,6 +157,11 @@ class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
 
     def images_to_codes(self, images):
         assert self.is_images_shaped(images), f"Images shape: {images.shape}"
+        # the reference re-tokenises through an 8-bit PIL image (chameleon_wrapper.py:176-183 -> image_tokenizer.py:100-114
+        # `_pil_from_chw_tensor`: clamp, (x + 1) / 2 * 255 TRUNCATED to uint8; :72-91 `_vqgan_input_from`: u8 / 255 * 2 - 1;
+        # resize and centre crop are the identity at the model's own resolution): same quantisation here, on the device
+        q = torch.floor((images.float().clamp(-1.0, 1.0) + 1.0) / 2.0 * 255.0)
+        images = (q / 255.0 * 2.0 - 1.0).to(images.dtype)
         codes = self.img2bpe[self._vqgan.encode(images)] + IMAGE_TOKEN_LO
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
         return codes

@@ -85,8 +85,8 @@ class GentimeWatermark:
             raise AssertionError("Spatial seeding only implemented for context size in [1,3]")
 
         # one table row per possible context SUM (only the sum enters the seed, gentime_watermark.py:225)
-        if self.seed_strategy is SeedStrategy.FIXED:
-            self.n_rows = 1
+        if self.seed_strategy is SeedStrategy.FIXED or self.context_size == 0:
+            self.n_rows = 1          # context_size 0: the context sum is always 0, only row 0 is reachable
         else:
             self.n_rows = max(self.context_size, 1) * (self.vocab_size - 1) + 1
         words = (self.vocab_size + 31) // 32
