@@ -89,6 +89,18 @@ typedef struct wmar_sample_params {
                          that (float)(1 - top_p) equals torch's scalar cast                        */
     int greedy;       /* 1: first arg-max of softmax (sample_logits=False, mingpt.py:360-361)      */
     uint64_t seed;    /* Philox key used when d_noise == NULL and !greedy                          */
+    /* rng_mode 1 (d_noise == NULL, !greedy): draw q exactly as torch.multinomial would on this device -- the Exp(1)
+     * tensor of `empty_like(probs).exponential_(1)` on torch's CUDA generator (ATen distribution_nullary_kernel:
+     * Philox4x32-10 keyed by the generator seed, subsequence = thread index of a 256-thread grid of
+     * min(SMs * threads_per_SM / 256, ceil(numel / 1024)) blocks, 4 values per Philox call, offset advancing by
+     * 4 * ceil(numel / (4 * threads)) per call).  seed = the generator's seed, torch_offset = its Philox offset before
+     * the first step, torch_threads = 256 * grid, torch_numel = rows * row length of the probability tensor
+     * (mingpt.py:363, rar.py:454, token_selector.py:26-47).  The caller advances the generator afterwards. */
+    int rng_mode;
+    int torch_threads;
+    uint64_t torch_offset;
+    int64_t torch_numel;
+    int64_t torch_rowlen;   /* row length of the probability tensor (the full vocabulary)              */
 } wmar_sample_params;
 
 /*
@@ -99,6 +111,11 @@ typedef struct wmar_sample_params {
 int wmar_wm_sample(const wmar_wm_params *wm, const wmar_sample_params *sp, const int64_t *d_past_ids, int64_t B,
                    int64_t t, int64_t past_stride, const float *d_logits, const float *d_noise, int64_t *d_out_ids,
                    void *stream);
+
+/* Test hook of rng_mode 1: d_out fp32 [rows][rowlen] = the Exp(1) tensor torch's CUDA generator in state (seed, offset)
+ * draws for `empty(rows, rowlen).exponential_(1)`; threads = 256 * min(SMs * max_threads_per_SM / 256, ceil(numel / 1024)). */
+int wmar_debug_torch_exponential(uint64_t seed, uint64_t offset, int64_t rows, int64_t rowlen, int threads, float *d_out,
+                                 void *stream);
 
 /* Reads and clears the device-side error flag set by the operators above (synchronises `stream`):
  * WMAR_OK, or WMAR_ERR_RANGE when a context sum fell outside the table / the top-p candidate set overflowed. */

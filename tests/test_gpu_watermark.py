@@ -195,3 +195,67 @@ def test_clustering_split_on_device_matches_reference_golden():
     assert torch.equal(out[0].cpu(), want) and torch.equal(out[1].cpu(), want)
     with pytest.raises(AssertionError):
         GentimeWatermark(vq, V, SeedStrategy.LINEAR, SplitStrategy.CLUSTERING, 1, 2.0, 0.5, device="cuda")
+
+
+@pytest.mark.parametrize("rows,rowlen", [(16, 16384), (8, 1024), (5, 65536), (3, 1000), (16, 100000)])
+def test_in_kernel_torch_philox_stream_is_bit_identical(rows, rowlen):
+    """rng_mode 1 of the sampler replicates torch's CUDA generator: the Exp(1) tensor that `torch.multinomial` divides by
+    (`empty_like(probs).exponential_(1)`, mingpt.py:363 / rar.py:454) is reproduced element by element, bit for bit, from
+    (seed, offset) -- including the generator's offset bookkeeping over consecutive calls and tensors large enough for
+    the grid-stride loop to use all four values of a Philox call."""
+    from wmar_b200 import _lib
+    from wmar_b200.models.armm_wrapper import AutoregressiveMultimodalModelWrapper
+
+    class W(AutoregressiveMultimodalModelWrapper):
+        device = torch.device("cuda", torch.cuda.current_device())
+
+    torch.manual_seed(1234 + rows)
+    torch.rand(7, device="cuda")                       # some earlier use of the generator
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    st = gen.get_state()
+    steps = 3
+    want = [torch.empty(rows, rowlen, device="cuda").exponential_(1) for _ in range(steps)]
+    end_offset = gen.get_offset()
+    gen.set_state(st)
+    p = W()._torch_stream(steps, rows, rowlen)
+    assert gen.get_offset() == end_offset              # the generator is advanced exactly like torch would have
+    iters = (p["torch_numel"] - 1) // (p["torch_threads"] * 4) + 1
+    for s in range(steps):
+        got = torch.empty(rows, rowlen, device="cuda")
+        _lib.check(_lib.lib().wmar_debug_torch_exponential(p["seed"], p["torch_offset"] + 4 * iters * s, rows, rowlen,
+                                                           p["torch_threads"], _lib.ptr(got), _lib.current_stream()))
+        assert torch.equal(got, want[s]), (s, (got != want[s]).sum().item())
+
+
+def test_wrapper_sampling_equals_torch_buffer_mode():
+    """TamingARMMWrapper / RarARMMWrapper: rng="torch" (stream drawn inside the sampler) and rng="torch_buffer" (the
+    same stream pre-drawn by torch, the round-1 path pinned to the reference goldens) give identical codes under the same
+    seed, and leave torch's generator in the same state."""
+    from oracle import gpt as ogpt
+    from oracle import vqgan as ov
+    from wmar_b200.models import RarARMMWrapper, TamingARMMWrapper
+    from wmar_b200.watermarking import create_watermarker_from_string
+    V, steps = 16384, 64
+    gpt_cfg = dict(vocab_size=V, block_size=steps, n_layer=2, n_head=4, n_embd=256)
+    dd = dict(ov.TAMING_CFG, ch=128, ch_mult=(1, 2), resolution=16, attn_resolutions=(8,))
+    gw = ogpt.synthetic_gpt_weights(V, steps, 2, 4, 256, seed=7)
+    vw = ov.synthetic_taming_vqgan_weights(dd, seed=8)
+    state = {"transformer." + k: v for k, v in gw.items()}
+    state.update({"first_stage_model." + k: v for k, v in vw.items()})
+    gp = {"temperature": 1.0, "top_k": 250, "top_p": 0.92}
+    out, tail = {}, {}
+    for rng in ("torch", "torch_buffer"):
+        m = TamingARMMWrapper(state_dict=state, gpt_cfg=gpt_cfg, dd_cfg=dd, device="cuda", max_batch=4, rng=rng)
+        wm = create_watermarker_from_string(m.get_vq(), V, "linear-stratifiedrand-h=1-d=2.0-g=0.25", "cuda")
+        m.set_watermarker(wm)
+        torch.manual_seed(11)
+        out[rng] = m.sample([1, 9, 232, 975, 3, 4], gp, apply_watermark=True).cpu()      # two engine calls (4 + 2 rows)
+        tail[rng] = torch.rand(4, device="cuda").cpu()
+    assert torch.equal(out["torch"], out["torch_buffer"]) and torch.equal(tail["torch"], tail["torch_buffer"])
+    out = {}
+    for rng in ("torch", "torch_buffer"):
+        m = RarARMMWrapper(rar_cfg=dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512),
+                           max_batch=4, rng=rng)
+        torch.manual_seed(12)
+        out[rng] = m.sample([1, 9, 232, 340, 975], None, apply_watermark=False).cpu()
+    assert torch.equal(out["torch"], out["torch_buffer"])

@@ -21,7 +21,9 @@ class WmParams(ctypes.Structure):
 
 class SampleParams(ctypes.Structure):
     _fields_ = [("temperature", ctypes.c_float), ("top_k", ctypes.c_int), ("top_p", ctypes.c_double),
-                ("greedy", ctypes.c_int), ("seed", ctypes.c_uint64)]
+                ("greedy", ctypes.c_int), ("seed", ctypes.c_uint64), ("rng_mode", ctypes.c_int),
+                ("torch_threads", ctypes.c_int), ("torch_offset", ctypes.c_uint64), ("torch_numel", ctypes.c_int64),
+                ("torch_rowlen", ctypes.c_int64)]
 
 
 class GptConfig(ctypes.Structure):
@@ -74,6 +76,8 @@ EXPORTS = {
                                        ctypes.c_int64, ctypes.c_int64, c_voidp, c_voidp, c_voidp, c_voidp]),
     "wmar_gpt_algorithmic_bytes": (ctypes.c_double, [c_voidp, ctypes.c_int64, ctypes.c_int64]),
     "wmar_gpt_launches_per_step": (ctypes.c_int, [c_voidp]),
+    "wmar_debug_torch_exponential": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64,
+                                                    ctypes.c_int, c_voidp, c_voidp]),
     "wmar_pstep_prog_bytes": (ctypes.c_int, []),
     "wmar_pstep_plan_debug": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_voidp,
                                              ctypes.POINTER(ctypes.c_longlong)]),

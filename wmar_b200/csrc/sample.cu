@@ -32,6 +32,11 @@ __global__ void __launch_bounds__(256) process_logits_kernel(const uint32_t *__r
     }
 }
 
+__global__ void torch_exp_fill_kernel(SampleArgs a, long long numel, float *__restrict__ out) {
+    const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li < numel) out[li] = torch_cuda_exp1(a, 0u, (unsigned)(li / a.torch_rowlen), (unsigned)(li % a.torch_rowlen));
+}
+
 __global__ void __launch_bounds__(SAMPLE_THREADS, 1) wm_sample_kernel(SampleArgs a, const float *__restrict__ logits,
                                                                        const int64_t *__restrict__ past, long long t,
                                                                        long long past_stride,
@@ -98,6 +103,15 @@ int make_sample_args(const wmar_wm_params *wm, const wmar_sample_params *sp, int
     a.top_k = sp->top_k;
     a.greedy = sp->greedy;
     a.seed = sp->seed;
+    a.rng_mode = sp->rng_mode;
+    if (sp->rng_mode == 1) {
+        WMAR_REQUIRE(sp->torch_threads > 0 && sp->torch_threads % 256 == 0 && sp->torch_numel > 0 && sp->torch_rowlen > 0 &&
+                     sp->torch_offset % 4 == 0, "bad torch generator replication parameters");
+        a.torch_threads = (unsigned)sp->torch_threads;
+        a.torch_iters = (unsigned)((sp->torch_numel - 1) / ((int64_t)sp->torch_threads * 4) + 1);
+        a.torch_offset = sp->torch_offset;
+        a.torch_rowlen = sp->torch_rowlen;
+    }
     const bool use_top_p = sp->top_p > 0.0 && sp->top_p < 1.0;
     a.top_p_threshold = use_top_p ? (float)(1.0 - sp->top_p) : -1.f;
     if (use_top_p) {
@@ -147,6 +161,19 @@ int wmar_wm_sample(const wmar_wm_params *wm, const wmar_sample_params *sp, const
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(wm_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wm_sample_kernel<<<(unsigned)B, SAMPLE_THREADS, smem, as_stream(stream)>>>(a, d_logits, d_past_ids, t, past_stride,
                                                                               d_noise, d_out_ids, cur_err_flag());
+    WMAR_LAUNCH_CHECK();
+    return WMAR_OK;
+}
+
+/* test hook: out[numel] = the Exp(1) tensor torch's CUDA generator (seed, offset) would draw for a [rows][rowlen] tensor
+ * on a device with `threads` = 256 * grid generator threads (rng_mode 1 of the sampler, element by element) */
+int wmar_debug_torch_exponential(uint64_t seed, uint64_t offset, int64_t rows, int64_t rowlen, int threads, float *d_out,
+                                 void *stream) {
+    WMAR_REQUIRE(d_out != nullptr && rows > 0 && rowlen > 0 && threads > 0 && threads % 256 == 0, "bad arguments");
+    SampleArgs a{};
+    a.seed = seed; a.rng_mode = 1; a.torch_threads = (unsigned)threads; a.torch_offset = offset; a.torch_rowlen = rowlen;
+    a.torch_iters = (unsigned)((rows * rowlen - 1) / ((int64_t)threads * 4) + 1);
+    torch_exp_fill_kernel<<<(unsigned)((rows * rowlen + 255) / 256), 256, 0, as_stream(stream)>>>(a, rows * rowlen, d_out);
     WMAR_LAUNCH_CHECK();
     return WMAR_OK;
 }

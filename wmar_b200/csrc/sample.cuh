@@ -29,6 +29,13 @@ struct SampleArgs {
     // logits_row / noise_row point at the window, the greenlist table still covers the full vocabulary table_V
     int id_base;   // 0 = no window
     int table_V;   // 0 = V
+    // rng_mode 1: replicate torch's CUDA generator (see wmar_sample_params): q of element (row b, column c) of the
+    // [rows][rowlen] tensor drawn at call `s` = transform(Philox(seed, subsequence = li % T, counter = offset / 4 +
+    // s * iters + (li / T) / 4)[(li / T) % 4]) with li = b * rowlen + c, T = torch_threads, iters = ceil(numel / 4T)
+    int rng_mode;
+    unsigned torch_threads, torch_iters;
+    unsigned long long torch_offset;
+    long long torch_rowlen;
 };
 
 __host__ __device__ inline size_t sample_smem_bytes(int V, int cand_cap) {
@@ -60,6 +67,29 @@ __device__ __forceinline__ float philox_exp1(unsigned long long seed, unsigned l
     }
     float u = ((float)(c0 >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
     return -logf(u);
+}
+
+// q ~ Exp(1) exactly as `empty_like(probs).exponential_(1)` yields it on torch's CUDA generator (ATen
+// DistributionTemplates.h distribution_nullary_kernel + transformation::exponential, curand Philox4_32_10 /
+// curand_uniform4): bit-identical to the tensor torch.multinomial divides by.
+__device__ __forceinline__ float torch_cuda_exp1(const SampleArgs &a, unsigned call, unsigned row, unsigned col) {
+    const unsigned long long li = (unsigned long long)row * (unsigned long long)a.torch_rowlen + col;
+    const unsigned T = a.torch_threads;
+    const unsigned idx = (unsigned)(li % T), q = (unsigned)(li / T);
+    const unsigned long long ctr = a.torch_offset / 4ull + (unsigned long long)call * a.torch_iters + (q >> 2);
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = idx, c3 = 0u;
+    uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const unsigned ii = q & 3u;
+    const uint32_t x = ii == 0 ? c0 : ii == 1 ? c1 : ii == 2 ? c2 : c3;
+    const float u = x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);            // _curand_uniform: (0, 1]
+    // at::log<float> on the device is the fast approximation __logf (ATen/NumericUtils.h:150-160), not logf
+    const float lg = u >= 1.0f - 1.1920928955078125e-07f / 2.0f ? -1.1920928955078125e-07f / 2.0f : __logf(u);
+    return -1.0f / 1.0f * lg;
 }
 
 // Block-wide arg-max with first-index tie break.  red_* : smem scratch of SAMPLE_WARPS entries each.
@@ -264,7 +294,10 @@ __device__ inline int sample_row(const SampleArgs &a, const float *__restrict__ 
         float sc;
         if (a.greedy) sc = p;
         else {
-            float q = noise_row != nullptr ? noise_row[v] : philox_exp1(a.seed, noise_stream, (uint32_t)v);
+            float q;
+            if (noise_row != nullptr) q = noise_row[v];
+            else if (a.rng_mode == 1) q = torch_cuda_exp1(a, (unsigned)(noise_stream >> 32), (unsigned)noise_stream, (unsigned)(v + a.id_base));
+            else q = philox_exp1(a.seed, noise_stream, (uint32_t)v);
             sc = p / q;
         }
         if (sc > best) { best = sc; best_i = v; }  // ascending v within a thread keeps the first index on ties

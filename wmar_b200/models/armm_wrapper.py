@@ -60,6 +60,23 @@ class AutoregressiveMultimodalModelWrapper:
                 and images.shape[2] == self.image_size and images.shape[3] == self.image_size)
 
     # -- shared by the subclasses ---------------------------------------------------------------------------
+    def _torch_stream(self, steps, rows, rowlen):
+        """Parameters that let the sampler kernel draw, element by element, the very Exp(1) tensors that `steps`
+        consecutive `torch.multinomial(probs[rows, rowlen], 1)` calls would draw from torch's CUDA generator on this device
+        (ATen DistributionTemplates.h: calc_execution_policy + distribution_elementwise_grid_stride_kernel), and advance
+        the generator past them -- a run seeded like the reference consumes the identical Philox stream, without the
+        [steps, rows, rowlen] noise buffer and its `steps` host-issued exponential_ launches."""
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        gen = torch.cuda.default_generators[idx]
+        props = torch.cuda.get_device_properties(idx)
+        numel = rows * rowlen
+        grid = min(props.multi_processor_count * (props.max_threads_per_multi_processor // 256), (numel + 255) // 256)
+        threads = 256 * grid
+        iters = (numel - 1) // (threads * 4) + 1
+        seed, offset = gen.initial_seed(), gen.get_offset()
+        gen.set_offset(offset + 4 * iters * steps)
+        return dict(seed=seed, torch_offset=offset, torch_threads=threads, torch_numel=numel, torch_rowlen=rowlen)
+
     def _draw_noise(self, steps, rows, vocab):
         """q ~ Exp(1) for every step, drawn from torch's CUDA generator with the SAME sequence of calls the reference
         makes (`torch.multinomial(probs, 1)` == `argmax(probs / empty_like(probs).exponential_(1))`, one call per

@@ -72,7 +72,7 @@ class ChameleonEngine:
 
     @torch.no_grad()
     def sample(self, prompts3, steps=1024, guidance_text=3.0, guidance_image=1.2, temperature=1.0, top_p=None,
-               watermarker=None, noise=None, greedy=False, seed=0, return_logits=False):
+               watermarker=None, noise=None, greedy=False, seed=0, return_logits=False, torch_stream=None):
         """prompts3: 3B token-id lists (B full-conditioned, B image-conditioned, B unconditioned rows, each ending in
         <boi>; chameleon.py:351-372).  Returns ids int64[B, steps] (+ the mixed logits of the image-token window)."""
         R = len(prompts3)
@@ -95,6 +95,10 @@ class ChameleonEngine:
         out = torch.empty((B, steps), dtype=torch.long, device=self.device)
         logits = torch.empty((steps, B, W), dtype=torch.float32, device=self.device) if return_logits else None
         sp = _lib.SampleParams(float(temperature), 0, float(top_p) if top_p else 0.0, 1 if greedy else 0, int(seed))
+        if torch_stream is not None and noise is None and not greedy:   # torch's own CUDA Philox stream, drawn in the kernel
+            sp.seed, sp.rng_mode = int(torch_stream["seed"]), 1
+            sp.torch_offset, sp.torch_threads = int(torch_stream["torch_offset"]), int(torch_stream["torch_threads"])
+            sp.torch_numel, sp.torch_rowlen = int(torch_stream["torch_numel"]), int(torch_stream["torch_rowlen"])
         wm = watermarker.c_params() if watermarker is not None else None
         if noise is not None:
             assert noise.shape == (steps, B, self.vocab_size) and noise.dtype == torch.float32 and noise.is_cuda

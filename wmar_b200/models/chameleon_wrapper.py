@@ -137,13 +137,16 @@ class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
         for i in range(0, len(prompts), mb):
             rows = self.prompt_rows(prompts[i:i + mb])
             b = len(rows) // 3
-            noise = None
-            if not greedy and self.rng == "torch":
+            noise, stream = None, None
+            if not greedy and self.rng == "torch":            # multinomial over probs[b, V] (token_selector.py:26-47)
+                stream = self._torch_stream(steps, b, V)
+            elif not greedy and self.rng == "torch_buffer":
                 noise = self._draw_noise(steps, b, V)
             self._step_seed += 1
             out.append(self._eng.sample(rows, steps, self.guidance_text, self.guidance_image,
                                         temperature=gen_params.get("temperature", 1.0), top_p=gen_params.get("top_p"),
-                                        watermarker=wm, noise=noise, greedy=greedy, seed=self._step_seed))
+                                        watermarker=wm, noise=noise, greedy=greedy, seed=self._step_seed,
+                                        torch_stream=stream))
         codes = out[0] if len(out) == 1 else torch.cat(out, dim=0)
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
         return codes

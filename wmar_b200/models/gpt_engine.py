@@ -63,7 +63,7 @@ class TamingGPTEngine:
 
     @torch.no_grad()
     def sample(self, cond, steps, temperature=1.0, top_k=None, top_p=None, watermarker=None, noise=None,
-               greedy=False, seed=0, return_logits=False):
+               greedy=False, seed=0, return_logits=False, torch_stream=None):
         """cond int64[B] -> codes int64[B, steps].  noise fp32[steps,B,V] ~ Exp(1) reproduces torch.multinomial's
         draws (see tests); None draws from an in-kernel Philox stream keyed by `seed`."""
         cond = torch.as_tensor(cond, dtype=torch.long, device=self.device).reshape(-1).contiguous()
@@ -72,6 +72,10 @@ class TamingGPTEngine:
         logits = torch.empty((steps, B, self.vocab_size), dtype=torch.float32, device=self.device) if return_logits else None
         sp = _lib.SampleParams(float(temperature), int(top_k) if top_k else 0, float(top_p) if top_p else 0.0,
                                1 if greedy else 0, int(seed))
+        if torch_stream is not None and noise is None and not greedy:   # torch's own CUDA Philox stream, drawn in the kernel
+            sp.seed, sp.rng_mode = int(torch_stream["seed"]), 1
+            sp.torch_offset, sp.torch_threads = int(torch_stream["torch_offset"]), int(torch_stream["torch_threads"])
+            sp.torch_numel, sp.torch_rowlen = int(torch_stream["torch_numel"]), int(torch_stream["torch_rowlen"])
         wm = watermarker.c_params() if watermarker is not None else None
         if noise is not None:
             assert noise.shape == (steps, B, self.vocab_size) and noise.dtype == torch.float32 and noise.is_cuda

@@ -71,7 +71,7 @@ class RAREngine:
 
     @torch.no_grad()
     def sample(self, cond, steps=None, guidance_scale=4.0, temperature=1.0, watermarker=None, noise=None, greedy=False,
-               seed=0, return_logits=False):
+               seed=0, return_logits=False, torch_stream=None):
         """cond int64[B] class ids -> ids int64[B, steps]; noise fp32[steps,B,V] ~ Exp(1) or None (in-kernel Philox)."""
         steps = steps or self.image_seq_len
         cond = torch.as_tensor(cond, dtype=torch.long, device=self.device).reshape(-1).contiguous()
@@ -80,6 +80,10 @@ class RAREngine:
         out = torch.empty((B, steps), dtype=torch.long, device=self.device)
         logits = torch.empty((steps, B, V), dtype=torch.float32, device=self.device) if return_logits else None
         sp = _lib.SampleParams(float(temperature), 0, 0.0, 1 if greedy else 0, int(seed))
+        if torch_stream is not None and noise is None and not greedy:   # torch's own CUDA Philox stream, drawn in the kernel
+            sp.seed, sp.rng_mode = int(torch_stream["seed"]), 1
+            sp.torch_offset, sp.torch_threads = int(torch_stream["torch_offset"]), int(torch_stream["torch_threads"])
+            sp.torch_numel, sp.torch_rowlen = int(torch_stream["torch_numel"]), int(torch_stream["torch_rowlen"])
         wm = watermarker.c_params() if watermarker is not None else None
         if noise is not None:
             assert noise.shape == (steps, B, V) and noise.dtype == torch.float32 and noise.is_cuda

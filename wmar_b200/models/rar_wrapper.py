@@ -98,14 +98,17 @@ class RarARMMWrapper(AutoregressiveMultimodalModelWrapper):
         mb = self._rar.max_batch
         for i in range(0, cond.numel(), mb):
             c = cond[i:i + mb]
-            noise = None
-            if not greedy and self.rng == "torch":
+            noise, stream = None, None
+            if not greedy and self.rng in ("torch", "torch_buffer"):
                 # RAR.preprocess_condition draws torch.rand_like(condition) first (rar.py:305)
                 torch.rand(c.shape, device=self.device)
-                noise = self._draw_noise(steps, c.numel(), V)
+                if self.rng == "torch":
+                    stream = self._torch_stream(steps, c.numel(), V)
+                else:
+                    noise = self._draw_noise(steps, c.numel(), V)
             self._step_seed += 1
             out.append(self._rar.sample(c, steps, guidance_scale=4.0, temperature=1.0, watermarker=wm, noise=noise,
-                                        greedy=greedy, seed=self._step_seed))
+                                        greedy=greedy, seed=self._step_seed, torch_stream=stream))
         codes = out[0] if len(out) == 1 else torch.cat(out, dim=0)
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
         return codes

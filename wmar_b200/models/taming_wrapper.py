@@ -41,8 +41,9 @@ class TamingARMMWrapper(AutoregressiveMultimodalModelWrapper):
                  vqgan_precision="3xtf32", seed=0, alive_ids_path=None, rng="torch"):
         """modelpath: directory of the reference's Taming download (README.md); None -> seeded random-init weights at
         ``gpt_cfg`` / ``dd_cfg`` shapes (default: the reference's cin_transformer shapes), or an explicit
-        ``state_dict`` with Net2NetTransformer keys.  rng: "torch" replays torch.multinomial's CUDA draws (same
-        seeds -> same stream as the reference), "philox" draws inside the kernel (no noise buffer)."""
+        ``state_dict`` with Net2NetTransformer keys.  rng: "torch" draws torch.multinomial's own CUDA Philox stream inside
+        the sampler kernel (same seeds -> same tokens as the reference, no noise buffer), "torch_buffer" lets torch pre-draw
+        that stream into a [steps, B, V] buffer (round 1), "philox" uses an independent in-kernel stream."""
         super().__init__()
         self._device = torch.device(device)
         if self._device.type != "cuda":
@@ -112,13 +113,15 @@ class TamingARMMWrapper(AutoregressiveMultimodalModelWrapper):
         out = []
         for i in range(0, cond.numel(), self.max_batch):
             c = cond[i:i + self.max_batch]
-            noise = None
-            if not greedy and self.rng == "torch":
+            noise, stream = None, None
+            if not greedy and self.rng == "torch":            # torch.multinomial's draws, generated inside the sampler
+                stream = self._torch_stream(steps, c.numel(), self.gpt_cfg["vocab_size"])
+            elif not greedy and self.rng == "torch_buffer":   # the same draws, pre-drawn by torch into a buffer
                 noise = self._draw_noise(steps, c.numel(), self.gpt_cfg["vocab_size"])
             self._step_seed += 1
             out.append(self._gpt.sample(c, steps, temperature=gen_params["temperature"], top_k=gen_params["top_k"],
                                         top_p=gen_params["top_p"], watermarker=wm, noise=noise, greedy=greedy,
-                                        seed=self._step_seed))
+                                        seed=self._step_seed, torch_stream=stream))
         codes = out[0] if len(out) == 1 else torch.cat(out, dim=0)
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
         return codes
