@@ -9,13 +9,20 @@ CPU restatement (torch, bf16 tensors like the reference model) of the Chameleon 
   * InBatchInstructCFGLogitsProcessor, AllowOnlyTokens  deps/chameleon/inference/logits_processor.py:312-335,135-151
   * ReplicatedInputTokenSelector                        deps/chameleon/inference/token_selector.py:26-47
 
-PARITY UNPINNED for the transformer: it depends on xformers (RMSNorm, rope_padded, fmha.memory_efficient_attention_forward,
-BlockDiagonalCausalWithOffsetPaddedKeysMask; unpinned in the reference's README.md:37), which is not installed here and
-has no tests or golden vectors in the reference.  The restatement follows the documented xformers semantics:
+Pinning of the transformer: tests/golden/chameleon_transformer.npz holds logits of the reference's OWN `Transformer` module
+(imported unmodified, built like loader.py:16-33) on ragged prefills + teacher-forced single-token passes, multi-head and
+grouped-query (oracle/gen_golden_chameleon_transformer.py); this restatement reproduces them to within single bf16
+rounding flips (tests/test_oracle_chameleon.py).  What that run could NOT execute are the three xformers operators the
+module imports (RMSNorm, rope_padded, fmha.memory_efficient_attention_forward with
+BlockDiagonalCausalWithOffsetPaddedKeysMask; xformers is unpinned in the reference's README.md:37, not installable here
+and has no CPU kernels): they came from oracle/xformers_stub, written from the documented semantics --
 RMSNorm = x * rsqrt(mean(x^2) + eps) * weight in fp32, stored in the input dtype; rope_padded rotates ADJACENT pairs
-(x[2j], x[2j+1]) by position * theta^(-2j/hd) in fp32, stores bf16 and appends k, v to the cache; attention is
-softmax(q k^T / sqrt(hd)) v over the row's own keys 0..p with fp32 softmax.  The logits processors / token selector ARE
-pinned: tests/golden/chameleon_sampling.npz is produced by the imported reference classes (oracle/gen_golden_chameleon.py).
+(x[2j], x[2j+1]) by position * theta^(-2j/hd) in fp32, stores bf16 and appends k, v to the padded cache; attention is
+softmax(q k^T / sqrt(hd)) v over the row's own keys 0..p with fp32 softmax.  So: module graph, fused-weight layouts, norm
+placement, GQA expansion, residual order and every bf16 rounding point of the Linear layers are PINNED to the reference
+run; the inside of those three operators is pinned to their documentation only ("parity unpinned" for them).
+The logits processors / token selector ARE pinned: tests/golden/chameleon_sampling.npz is produced by the imported
+reference classes (oracle/gen_golden_chameleon.py).
 """
 import math
 

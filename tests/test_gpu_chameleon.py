@@ -98,6 +98,45 @@ def test_chameleon_engine_vs_oracle_teacher_forced():
     _lib.check(_lib.lib().wmar_check_device_flag(_lib.current_stream()))
 
 
+@pytest.mark.parametrize("name", ["tiny", "gqa"])
+def test_chameleon_engine_vs_reference_module_logits(name):
+    """The CUDA engine against logits of the reference's OWN Transformer module (tests/golden/chameleon_transformer.npz,
+    oracle/gen_golden_chameleon_transformer.py): ragged prompts, three guidance groups, teacher-forced tokens.  Teacher
+    forcing goes through the public noise argument: q = 1e-30 at the forced id makes argmax(p / q) select it."""
+    from oracle import chameleon as oc
+    from wmar_b200 import _lib
+    from wmar_b200.models.cham_engine import ChameleonEngine
+    g = np.load(os.path.join(G, "chameleon_transformer.npz"))
+    V, d, L, H, Hkv, Fh, steps, seed = [int(x) for x in g[f"{name}/meta"]]
+    lens = [int(x) for x in g[f"{name}/prompt_lens"]]
+    flat = [int(x) for x in g[f"{name}/prompts_flat"]]
+    prompts3, o = [], 0
+    for n in lens:
+        prompts3.append(flat[o:o + n])
+        o += n
+    B = len(prompts3) // 3
+    forced = torch.from_numpy(g[f"{name}/forced"])[:B]                     # [B, steps]
+    ref = torch.from_numpy(g[f"{name}/logits"])                            # [steps + 1, 3B, V] fp32 (bf16 values)
+    lo, hi = 4, 516
+    w = oc.synthetic_chameleon_weights(V, d, L, H, Hkv, Fh, seed=seed)
+    eng = ChameleonEngine(w, L, H, n_kv_head=Hkv, image_tokens=(lo, hi), max_seq=64, max_batch=2)
+    noise = torch.ones(steps + 1, B, V)
+    for s in range(steps):
+        noise[s, torch.arange(B), forced[:, s]] = 1e-30
+    ids, mixed = eng.sample(prompts3, steps + 1, 3.0, 1.2, temperature=1.0, top_p=None, noise=noise.cuda(), return_logits=True)
+    np.testing.assert_array_equal(ids.cpu()[:, :steps].numpy(), forced.numpy())
+    f, im, u = ref[:, :B], ref[:, B:2 * B], ref[:, 2 * B:]
+    want = (u + 1.2 * (im - u) + 3.0 * (f - im))[:, :, lo:hi]              # logits_processor.py:312-335
+    got = mixed.cpu()
+    scale = want.abs().max().item()
+    err = (got - want).abs().max().item()
+    rms = (got - want).pow(2).mean().sqrt().item()
+    print(f"chameleon {name}: range {scale:.2f}, max |diff| {err:.4f}, rms {rms:.5f}")
+    # bf16 model, guidance scales 3.0 / 1.2 amplify single-ulp flips of the three rows (see the teacher-forced test above)
+    assert err <= 0.04 * scale and rms <= 0.004 * scale, (err, rms, scale)
+    _lib.check(_lib.lib().wmar_check_device_flag(_lib.current_stream()))
+
+
 def test_chameleon_engine_sampling_with_reference_noise_and_watermark():
     """Sampling path: with the Exp(1) draws of torch.multinomial and a fixed greenlist the engine's token at every step
     equals what the restated reference pipeline selects from the ENGINE's own mixed logits (isolates the fused
