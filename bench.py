@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
-    ap.add_argument("--vqgan-precision", choices=["3xtf32", "tf32"], default="3xtf32")
+    ap.add_argument("--vqgan-precision", choices=["3xtf32", "tf32", "bf16x3", "bf16x3-dec"], default="3xtf32")
     ap.add_argument("--rng", choices=["torch", "philox"], default="torch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)

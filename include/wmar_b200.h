@@ -286,7 +286,10 @@ typedef struct wmar_vqgan_config {
     int embed_dim;         /* codebook vector dim (256)                                                    */
     int n_embed;           /* codebook size                                                                */
     int max_batch;
-    int precision;         /* 0 = 3xTF32 (fp32-faithful), 1 = 1xTF32 (the reference's cuDNN default)       */
+    int precision;         /* 0 = 3xTF32 (fp32-faithful), 1 = 1xTF32 (the reference's cuDNN default),
+                              2 = bf16x3 on the tcgen05 3x3 convs (x = x1 + x2 in bf16, three kind::f16 products:
+                                  half the tensor time of 3xTF32, ~2^-17 per product), other convs 3xTF32,
+                              3 = 2 for the decoder, 0 for the encoder (detection keeps fp32-faithful codes)     */
 } wmar_vqgan_config;
 
 typedef struct wmar_vqgan wmar_vqgan;

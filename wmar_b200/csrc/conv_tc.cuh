@@ -201,6 +201,248 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// bf16x3 variant (wmar_vqgan_config.precision >= 2), persistent, epilogue overlapped with the next tile's MMAs.
+//
+// Same implicit GEMM, but every fp32 value is split into TWO bf16 terms (x = x1 + x2 + O(2^-18 |x|), both rounded to
+// nearest) and the product is x1.w1 + x1.w2 + x2.w1 on tcgen05.mma.kind::f16 -- K = 16 per instruction at the K = 8 cost of
+// kind::tf32, i.e. half the tensor time of the 3xTF32 kernel at ~2^-17 relative error per product (3xTF32: ~2^-21,
+// one TF32 product as cuDNN's default: 2^-11).  Differences to the kernel above:
+//   * a chunk is 64 channels of one tap: two 4-D TMA boxes of 32 fp32 channels (A raw, 2 x 16 KB) + the bf16 weight tiles
+//     w1 and w2 (128 rows x 64 k x 2 B = 16 KB each, SWIZZLE_128B like before); 3 ring stages of 64 KB,
+//   * converter warps pack (k, k+1) pairs into one 32-bit TMEM column: 32 columns x1 + 32 columns x2 per chunk,
+//   * all three products accumulate into ONE 128-column fp32 accumulator (three N = 128 MMAs per k16 step: the same
+//     tensor time as N = 256 + N = 128), which leaves room for TWO accumulators in tensor memory,
+//   * the CTA is persistent: tiles blockIdx.x, + gridDim.x, ...; the epilogue of tile i (TMEM -> registers -> bias /
+//     residual -> global) runs while the MMAs of tile i + 1 fill the other accumulator, and TMEM allocation, barrier
+//     initialisation and descriptor prefetch are paid once per SM instead of once per tile.
+constexpr int CB_NS = 3;                      // ring stages: A raw 32 KB + w1 16 KB + w2 16 KB each
+constexpr int CB_NTA = 4;                     // TMEM stages of split A
+constexpr int CB_STAGE_BYTES = 4 * CT_TILE_BYTES;
+constexpr int CB_TMEM_A0 = 256;               // cols [0,128) accumulator 0, [128,256) accumulator 1, [256,512) 4 A stages x 64
+constexpr int CB_SM_BAR = CB_NS * CB_STAGE_BYTES;
+constexpr int CB_N_BARS = 2 * CB_NS + 2 * CB_NTA + 4;
+constexpr int CB_SM_MISC = CB_SM_BAR + 8 * CB_N_BARS;
+constexpr int CB_SM_BYTES = CB_SM_MISC + 16;
+constexpr int CB_SM_ALLOC = CB_SM_BYTES + 1024;
+static_assert(CB_SM_ALLOC <= 232448, "conv_tc bf16 kernel exceeds 227 KB of shared memory");
+
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_bf16_m128(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// (x0, x1) -> packed bf16 pair of the leading terms (x0 in the low half) and of the remainders
+__device__ __forceinline__ void split_bf16_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+
+struct ConvTcTiles {
+    int n_tiles;     // B * tiles_x * tiles_y * (Cout / 128)
+    int nblk;        // Cout / 128 (fastest-varying: the CTAs that share an activation tile run back to back)
+    int dbg;         // probe only (WMAR_CB_DBG): bit 0 skips x1.w2, bit 1 skips x2.w1
+};
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv3x3_tc_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW1,
+                       const __grid_constant__ CUtensorMap mapW2, const ConvTcArgs a, const ConvTcTiles tl) {
+    using namespace tc05;
+    extern __shared__ uint8_t ct_smem_raw[];
+    const uint32_t smem_base = (smem_u32(ct_smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = ct_smem_raw + (smem_base - smem_u32(ct_smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tpi = a.tiles_x * a.tiles_y;
+    const int cchunks = a.Cin / 64, nchunks = 9 * cchunks;
+
+    const uint32_t bar0 = smem_base + CB_SM_BAR;
+    auto s_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto s_empty = [&](int s) { return bar0 + 8u * (uint32_t)(CB_NS + s); };
+    auto ta_full = [&](int u) { return bar0 + 8u * (uint32_t)(2 * CB_NS + u); };
+    auto ta_empty = [&](int u) { return bar0 + 8u * (uint32_t)(2 * CB_NS + CB_NTA + u); };
+    auto acc_full = [&](int k) { return bar0 + 8u * (uint32_t)(2 * CB_NS + 2 * CB_NTA + k); };
+    auto acc_empty = [&](int k) { return bar0 + 8u * (uint32_t)(2 * CB_NS + 2 * CB_NTA + 2 + k); };
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + CB_SM_MISC);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapW1);
+        tma_prefetch_desc(&mapW2);
+        for (int s = 0; s < CB_NS; s++) { mbar_init(s_full(s), 1); mbar_init(s_empty(s), 9); }
+        for (int u = 0; u < CB_NTA; u++) { mbar_init(ta_full(u), 8); mbar_init(ta_empty(u), 1); }
+        for (int k = 0; k < 2; k++) { mbar_init(acc_full(k), 1); mbar_init(acc_empty(k), 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(smem_u32(s_tmem));
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+
+    auto tile_coords = [&](int tile, int &b, int &x0, int &y0, int &n0) {
+        const int nb = tile % tl.nblk, pt = tile / tl.nblk;
+        b = pt / tpi;
+        const int tr = pt - b * tpi, ty = tr / a.tiles_x, tx = tr - ty * a.tiles_x;
+        x0 = tx * a.bw; y0 = ty * a.bh; n0 = nb * 128;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < tl.n_tiles; tile += gridDim.x) {
+                int b, x0, y0, n0;
+                tile_coords(tile, b, x0, y0, n0);
+                for (int c = 0; c < nchunks; c++, g++) {
+                    const uint32_t s = g % CB_NS;
+                    const int tap = c / cchunks, ci0 = (c - tap * cchunks) * 64;
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    mbar_wait(s_empty(s), ((g / CB_NS) & 1) ^ 1);
+                    mbar_arrive_expect_tx(s_full(s), CB_STAGE_BYTES);
+                    const uint32_t dst = smem_base + s * CB_STAGE_BYTES;
+                    tma_load_4d(dst, &mapA, ci0, x0 + kx - 1, y0 + ky - 1, b, s_full(s));           // zero fill = padding
+                    tma_load_4d(dst + CT_TILE_BYTES, &mapA, ci0 + 32, x0 + kx - 1, y0 + ky - 1, b, s_full(s));
+                    tma_load_2d(dst + 2 * CT_TILE_BYTES, &mapW1, tap * a.Cin + ci0, n0, s_full(s), L2_EVICT_LAST);
+                    tma_load_2d(dst + 3 * CT_TILE_BYTES, &mapW2, tap * a.Cin + ci0, n0, s_full(s), L2_EVICT_LAST);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t ID = idesc_bf16_m128(128);
+            uint32_t g = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < tl.n_tiles; tile += gridDim.x, it++) {
+                const uint32_t acc = tmem + (uint32_t)(it & 1) * 128u;
+                mbar_wait(acc_empty(it & 1), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+                fence_after_sync();
+                for (int c = 0; c < nchunks; c++, g++) {
+                    const uint32_t s = g % CB_NS, u = g % CB_NTA;
+                    mbar_wait(s_full(s), (g / CB_NS) & 1);          // the weight tiles of this stage have landed
+                    mbar_wait(ta_full(u), (g / CB_NTA) & 1);        // the split activations are in tensor memory
+                    fence_after_sync();
+                    const uint32_t a_hi = tmem + CB_TMEM_A0 + u * 64, a_lo = a_hi + 32;
+                    const uint32_t wb = smem_base + s * CB_STAGE_BYTES + 2 * CT_TILE_BYTES;   // w1 tile, w2 tile 16 KB further
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const uint64_t d1 = tc05::smem_desc_kmajor_sw128(wb + ks * 32);
+                        const uint64_t d2 = tc05::smem_desc_kmajor_sw128(wb + CT_TILE_BYTES + ks * 32);
+                        mma_bf16_ts(acc, a_hi + ks * 8, d1, ID, (c | ks) != 0 ? 1u : 0u);   // x1 . w1
+                        if (!(tl.dbg & 1)) mma_bf16_ts(acc, a_hi + ks * 8, d2, ID, 1u);       // x1 . w2
+                        if (!(tl.dbg & 2)) mma_bf16_ts(acc, a_lo + ks * 8, d1, ID, 1u);       // x2 . w1
+                    }
+                    mma_commit(ta_empty(u));
+                    mma_commit(s_empty(s));
+                }
+                mma_commit(acc_full(it & 1));
+            }
+        }
+        __syncwarp();
+    } else if (warp < CT_W_EPI) {
+        // ===================== activation converters (thread <-> pixel <-> TMEM lane) =====================
+        // warps 2-5 convert channels 0-31 of every chunk, warps 6-9 channels 32-63: EVERY converter warp waits for EVERY
+        // phase of every ring barrier (a warp that skipped phases could be satisfied by the wrong phase: try_wait only
+        // sees the parity bit -- with 3 stages and two alternating groups a stage would alternate between the groups)
+        const int h = (warp - CT_W_CONV) >> 2;
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < tl.n_tiles; tile += gridDim.x) {
+            for (int c = 0; c < nchunks; c++, g++) {
+                const uint32_t s = g % CB_NS, u = g % CB_NTA;
+                mbar_wait_warp(s_full(s), (g / CB_NS) & 1, lane);
+                const uint8_t *arow = smem + s * CB_STAGE_BYTES + h * CT_TILE_BYTES + r * 128;
+                float4 w4[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) w4[k] = *reinterpret_cast<const float4 *>(arow + ((k ^ (r & 7)) << 4));
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    split_bf16_pair(w4[k].x, w4[k].y, hi[2 * k], lo[2 * k]);
+                    split_bf16_pair(w4[k].z, w4[k].w, hi[2 * k + 1], lo[2 * k + 1]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty(s));          // the raw tile is in registers
+                mbar_wait_warp(ta_empty(u), ((g / CB_NTA) & 1) ^ 1, lane);
+                fence_after_sync();
+                const uint32_t a_hi = t_lane + CB_TMEM_A0 + u * 64 + h * 16, a_lo = a_hi + 32;
+                tmem_st16(a_hi, hi);
+                tmem_st16(a_lo, lo);
+                wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ta_full(u));
+            }
+        }
+    } else {
+        // ===================== epilogue (thread <-> pixel) =====================
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tl.n_tiles; tile += gridDim.x, it++) {
+            int b, x0, y0, n0;
+            tile_coords(tile, b, x0, y0, n0);
+            const int py = y0 + r / a.bw, px = x0 + r % a.bw;
+            const size_t pix = ((size_t)b * a.H + py) * a.W + px;
+            float *dst = a.out + pix * a.Cout + n0;
+            const float *res = a.resid != nullptr ? a.resid + pix * a.Cout + n0 : nullptr;
+            const uint32_t acc = t_lane + (uint32_t)(it & 1) * 128u;
+            mbar_wait_warp(acc_full(it & 1), (it >> 1) & 1, lane);
+            fence_after_sync();
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t d0[32];
+                tmem_ld32(acc + c0, d0);
+                wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + c0 + k));
+                    float4 v;
+                    v.x = __uint_as_float(d0[k]) + bb.x;
+                    v.y = __uint_as_float(d0[k + 1]) + bb.y;
+                    v.z = __uint_as_float(d0[k + 2]) + bb.z;
+                    v.w = __uint_as_float(d0[k + 3]) + bb.w;
+                    if (res != nullptr) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(res + c0 + k);
+                        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+                    }
+                    *reinterpret_cast<float4 *>(dst + c0 + k) = v;
+                }
+            }
+            // every TMEM read of this accumulator has completed (wait_ld above): hand it back to the MMA issuer
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(it & 1));
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// w -> (w1, w2) bf16 planes: w1 = bf16_rn(w), w2 = bf16_rn(w - w1)
+__global__ void conv_tc_wsplit_bf16_kernel(const float *__restrict__ w, uint16_t *__restrict__ w1, uint16_t *__restrict__ w2, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = w[i];
+        uint32_t hi, lo;
+        split_bf16_pair(x, 0.f, hi, lo);
+        w1[i] = (uint16_t)(hi & 0xffffu);
+        w2[i] = (uint16_t)(lo & 0xffffu);
+    }
+}
+
 // w_lo = w - trunc_tf32(w): the part of the weight the tensor core drops when it reads fp32 bits as TF32
 __global__ void conv_tc_wlo_kernel(const float *__restrict__ w, float *__restrict__ wlo, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

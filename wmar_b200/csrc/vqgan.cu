@@ -33,10 +33,13 @@ struct Op {
     int Hs, Ws, Cin, Ho, Wo, Cout, Cout_pad, ks, stride, pad, up;
     int final_out;  // decoder conv_out: NCHW + clamp into the caller's image
     float *wlo;     // tcgen05 path (conv_tc.cuh): w - trunc_tf32(w), same layout as w; null = mma.sync kernel
+    uint16_t *wb1, *wb2;   // tcgen05 bf16x3 path: bf16 planes w1 = rn(w), w2 = rn(w - w1); null = 3xTF32 kernel
     int tmp;        // up convs on the tcgen05 path: buffer that receives the materialised nearest x2 input
-    // gn
+    // gn (conv: gamma / beta of the GroupNorm fused into the decoder-tail kernel, fused_gn = 1)
     const float *gamma, *beta;
     int swish, H, W, C;
+    int stats_only;   // gn: only the statistics pass runs, the consumer (conv_out3_kernel) normalises while staging
+    int fused_gn;
     // attn: q,k,v buffers
     int bq, bk, bv;
 };
@@ -91,7 +94,7 @@ struct Builder {
         o.Ho = stride == 2 ? Hl / 2 : Hl;
         o.Wo = stride == 2 ? Wl / 2 : Wl;
         o.Cout = cout; o.Cout_pad = round_up(cout, 64);
-        o.ks = ks; o.stride = stride; o.pad = pad; o.up = up; o.final_out = final_out ? 1 : 0; o.tmp = -1; o.wlo = nullptr;
+        o.ks = ks; o.stride = stride; o.pad = pad; o.up = up; o.final_out = final_out ? 1 : 0; o.tmp = -1; o.wlo = nullptr; o.wb1 = o.wb2 = nullptr;
         ops->push_back(o);
         flops += 2.0 * o.Ho * o.Wo * (double)cout * (double)(ks * ks) * (double)C;
         H = o.Ho; W = o.Wo; C = cout;
@@ -243,6 +246,13 @@ int build_plans(wmar_vqgan *v, const void *const *tab, int n) {
         int t1 = b.free_buf({b.x});
         b.gn(b.x, t1, 1);
         b.conv(t1, -1, -1, 3, 3, 1, 1, 0, true);
+        // decoder tail as one fp32 kernel (conv_out3_kernel): GroupNorm + swish applied while the conv stages its input
+        const char *e = getenv("WMAR_CONVOUT");
+        if (!(e && e[0] == 'v') && b.ops->back().C % 32 == 0) {
+            Op &cv = b.ops->back(), &g = (*b.ops)[b.ops->size() - 2];
+            g.stats_only = 1;
+            cv.fused_gn = 1; cv.src = g.src; cv.gamma = g.gamma; cv.beta = g.beta;
+        }
     }
     v->flops_dec = b.flops;
     WMAR_REQUIRE(b.cur.pos == n, "weight table length does not match the architecture");
@@ -297,6 +307,26 @@ int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
     CUtensorMap mA, mWh, mWl;
     int rc;
     if ((rc = tc_nhwc_map(src, B, o.Ho, o.Wo, o.Cin, a.bw, a.bh, &mA))) return rc;
+    if (o.wb1 != nullptr) {
+        // bf16x3: persistent kernel, one CTA per SM walking the (pixel tile, 128-channel block) list
+        static bool configured_b = false;
+        if (!configured_b) {
+            WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SM_ALLOC));
+            configured_b = true;
+        }
+        if ((rc = tc_weight_map_bf16(o.wb1, o.Cout_pad, 9 * o.Cin, &mWh))) return rc;
+        if ((rc = tc_weight_map_bf16(o.wb2, o.Cout_pad, 9 * o.Cin, &mWl))) return rc;
+        ConvTcTiles tl{};
+        tl.nblk = o.Cout / 128;
+        tl.n_tiles = B * a.tiles_x * a.tiles_y * tl.nblk;
+        { const char *e = getenv("WMAR_CB_DBG"); tl.dbg = e ? atoi(e) : 0; }
+        static int sms = 0;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        const int grid = tl.n_tiles < sms ? tl.n_tiles : sms;
+        conv3x3_tc_bf16_kernel<<<grid, CT_THREADS, CB_SM_ALLOC, s>>>(mA, mWh, mWl, a, tl);
+        WMAR_LAUNCH_CHECK();
+        return WMAR_OK;
+    }
     if ((rc = tc_weight_map(o.w, o.Cout_pad, 9 * o.Cin, &mWh))) return rc;
     if ((rc = tc_weight_map(o.wlo, o.Cout_pad, 9 * o.Cin, &mWl))) return rc;
     dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)(o.Cout / 128));
@@ -305,8 +335,23 @@ int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
     return WMAR_OK;
 }
 
+int gn_chunks(int HW, int C);
+
 int run_conv(const wmar_vqgan *v, const Op &o, int B, float *final_out, cudaStream_t s) {
     if (o.wlo != nullptr) return run_conv_tc(v, o, B, s);
+    if (o.fused_gn) {
+        ConvOutArgs a{};
+        a.x = v->buf[o.src]; a.w = o.w; a.bias = o.b; a.out = final_out;
+        a.H = o.Ho; a.W = o.Wo; a.C = o.C;
+        a.gn_partial = v->gn_partial; a.nchunk = gn_chunks(o.Ho * o.Wo, o.C);
+        a.gamma = o.gamma; a.beta = o.beta; a.eps = 1e-6f;
+        a.out_scale = 1.f; a.out_shift = 0.f; a.clamp_lo = -1.f; a.clamp_hi = 1.f;
+        if (v->cfg.family == 1) { a.clamp_lo = 0.f; a.clamp_hi = 1.f; a.out_scale = 2.f; a.out_shift = -1.f; }
+        dim3 grid((unsigned)((o.Wo + CO_T - 1) / CO_T), (unsigned)((o.Ho + CO_T - 1) / CO_T), (unsigned)B);
+        conv_out3_kernel<<<grid, CO_T * CO_T, CO_SMEM_BYTES, s>>>(a);
+        WMAR_LAUNCH_CHECK();
+        return WMAR_OK;
+    }
     ConvArgs a{};
     a.in = v->buf[o.src]; a.w = o.w; a.bias = o.b;
     a.resid = o.res >= 0 ? v->buf[o.res] : nullptr;
@@ -323,7 +368,7 @@ int run_conv(const wmar_vqgan *v, const Op &o, int B, float *final_out, cudaStre
     WMAR_REQUIRE(M % CV_BM == 0, "B*Ho*Wo must be a multiple of 128");
     dim3 grid((unsigned)(M / CV_BM), (unsigned)(o.Cout_pad / CV_BN));
     const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
-    if (v->cfg.precision == 0) conv_igemm_kernel<1><<<grid, CV_THREADS, smem, s>>>(a);
+    if (v->cfg.precision != 1) conv_igemm_kernel<1><<<grid, CV_THREADS, smem, s>>>(a);
     else conv_igemm_kernel<0><<<grid, CV_THREADS, smem, s>>>(a);
     WMAR_LAUNCH_CHECK();
     return WMAR_OK;
@@ -346,6 +391,7 @@ int run_ops(const wmar_vqgan *v, const std::vector<Op> &ops, int B, float *final
                 const int HW = o.H * o.W, nchunk = gn_chunks(HW, o.C);
                 gn_partial_kernel<<<dim3(nchunk, B), GN_THREADS, 0, s>>>(v->buf[o.src], HW, o.C, nchunk, v->gn_partial);
                 WMAR_LAUNCH_CHECK();
+                if (o.stats_only) break;
                 long long total4 = (long long)HW * o.C / 4;
                 int gx = (int)((total4 + 255) / 256);
                 if (gx > 1024) gx = 1024;
@@ -384,7 +430,7 @@ int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights
     WMAR_REQUIRE(cfg->ch % 128 == 0, "base channel count must be a multiple of 128 (GroupNorm kernel: >= 4 channels/group)");
     WMAR_REQUIRE(cfg->z_channels % 32 == 0 && cfg->embed_dim % 32 == 0 && cfg->n_embed % 64 == 0, "bad latent dims");
     WMAR_REQUIRE(cfg->max_batch >= 1, "max_batch must be >= 1");
-    WMAR_REQUIRE(cfg->precision == 0 || cfg->precision == 1, "precision must be 0 (3xTF32) or 1 (TF32)");
+    WMAR_REQUIRE(cfg->precision >= 0 && cfg->precision <= 3, "precision must be 0 (3xTF32), 1 (TF32), 2 (bf16x3) or 3 (bf16x3 decoder, 3xTF32 encoder)");
     for (int i = 0; i < n_weights; i++) WMAR_REQUIRE(d_weights[i] != nullptr, "NULL weight pointer");
     wmar_vqgan *v = new (std::nothrow) wmar_vqgan();
     if (!v) return set_error(WMAR_ERR_NOMEM, "out of host memory%s%s");
@@ -425,12 +471,20 @@ int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights
                 WMAR_CUDA_CHECK(cudaMalloc(&o.wlo, sizeof(float) * nw));
                 conv_tc_wlo_kernel<<<1024, 256>>>(o.w, o.wlo, nw);
                 WMAR_LAUNCH_CHECK();
+                const bool bf = cfg->precision == 2 || (cfg->precision == 3 && ops == &v->dec);
+                if (bf && o.Cin % 64 == 0) {
+                    WMAR_CUDA_CHECK(cudaMalloc(&o.wb1, sizeof(uint16_t) * nw));
+                    WMAR_CUDA_CHECK(cudaMalloc(&o.wb2, sizeof(uint16_t) * nw));
+                    conv_tc_wsplit_bf16_kernel<<<1024, 256>>>(o.w, o.wb1, o.wb2, nw);
+                    WMAR_LAUNCH_CHECK();
+                }
             }
     }
     const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(attn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_out3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CO_SMEM_BYTES));
     WMAR_CUDA_CHECK(cudaDeviceSynchronize());
     *out = v;
     return WMAR_OK;
@@ -440,7 +494,7 @@ void wmar_vqgan_destroy(wmar_vqgan *v) {
     if (!v) return;
     cudaDeviceSynchronize();
     for (auto *ops : {&v->enc, &v->dec})
-        for (Op &o : *ops) cudaFree(o.wlo);
+        for (Op &o : *ops) { cudaFree(o.wlo); cudaFree(o.wb1); cudaFree(o.wb2); }
     for (int i = 0; i < 6; i++) cudaFree(v->buf[i]);
     cudaFree(v->dots); cudaFree(v->zz); cudaFree(v->ee); cudaFree(v->gn_partial);
     delete v;

@@ -97,6 +97,103 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float *__restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------- decoder tail
+// norm_out -> swish -> conv_out (C -> 3, 3x3, pad 1) -> clamp -> NCHW image, one kernel (model.py:533-538,
+// maskgit_vqgan.py decoder tail).  As an implicit GEMM this layer wastes the tensor tile (N = 3 of 64 columns: 3.4 ms per
+// 16 images at 256^2); it is a 3-row GEMV per pixel, so it runs on the fp32 FMA pipe: a CTA owns a 16 x 16 pixel tile,
+// stages the 18 x 18 halo of 32 channels at a time in shared memory (GroupNorm + swish applied while staging, zeros outside
+// the image = the conv's padding of the ACTIVATED tensor) and every thread accumulates its pixel's 3 outputs in plain
+// fp32 (no TF32 split needed).  Pixel stride 36 floats: the 8 lanes of an LDS.128 phase hit 8 different bank quads.
+constexpr int CO_T = 16, CO_HALO = CO_T + 2, CO_CH = 32, CO_LD = CO_CH + 4;
+constexpr int CO_SMEM_BYTES = (CO_HALO * CO_HALO * CO_LD + 3 * 9 * CO_CH) * 4;
+struct ConvOutArgs {
+    const float *x;          // NHWC [B][H][W][C], input of the GroupNorm
+    const float *w;          // [>= 3][3][3][C]
+    const float *bias;
+    float *out;              // NCHW [B][3][H][W]
+    int H, W, C;
+    const double2 *gn_partial; int nchunk;     // statistics of gn_partial_kernel over x
+    const float *gamma, *beta; float eps;
+    float clamp_lo, clamp_hi, out_scale, out_shift;
+};
+__global__ void __launch_bounds__(CO_T * CO_T) conv_out3_kernel(const ConvOutArgs a) {
+    extern __shared__ __align__(16) float co_smem[];
+    float *tile = co_smem;                                   // [18 * 18][CO_LD]
+    float *wsm = co_smem + CO_HALO * CO_HALO * CO_LD;        // [3][9][CO_CH]
+    __shared__ float s_mean[32], s_rstd[32];
+    const int tid = threadIdx.x, tx = tid % CO_T, ty = tid / CO_T;
+    const int b = blockIdx.z, x0 = blockIdx.x * CO_T, y0 = blockIdx.y * CO_T;
+    const int HW = a.H * a.W, cg = a.C / 32;
+    if (tid < 32) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int c = 0; c < a.nchunk; c++) {
+            const double2 p = a.gn_partial[((size_t)b * a.nchunk + c) * 32 + tid];
+            a0 += p.x; a1 += p.y;
+        }
+        const double n = (double)HW * cg;
+        const double mean = a0 / n;
+        double var = a1 / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[tid] = (float)mean;
+        s_rstd[tid] = (float)(1.0 / sqrt(var + (double)a.eps));
+    }
+    float acc[3] = {0.f, 0.f, 0.f};
+    const float *xb = a.x + (size_t)b * HW * a.C;
+    for (int c0 = 0; c0 < a.C; c0 += CO_CH) {
+        __syncthreads();   // statistics visible (first pass) / previous chunk consumed
+        // stage: 324 halo pixels x 8 channel quads
+        for (int i = tid; i < CO_HALO * CO_HALO * (CO_CH / 4); i += CO_T * CO_T) {
+            const int q = i % (CO_CH / 4), p = i / (CO_CH / 4);
+            const int hy = p / CO_HALO, hx = p - hy * CO_HALO;
+            const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+                const int c = c0 + 4 * q;
+                const float4 v = *reinterpret_cast<const float4 *>(xb + ((size_t)gy * a.W + gx) * a.C + c);
+                const float4 g4 = *reinterpret_cast<const float4 *>(a.gamma + c);
+                const float4 b4 = *reinterpret_cast<const float4 *>(a.beta + c);
+                const float mean = s_mean[c / cg], rstd = s_rstd[c / cg];   // a quad never straddles a group (cg >= 4)
+                float t[4] = {(v.x - mean) * rstd * g4.x + b4.x, (v.y - mean) * rstd * g4.y + b4.y,
+                              (v.z - mean) * rstd * g4.z + b4.z, (v.w - mean) * rstd * g4.w + b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) t[e] = t[e] * (1.0f / (1.0f + expf(-t[e])));
+                o = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            *reinterpret_cast<float4 *>(tile + p * CO_LD + 4 * q) = o;
+        }
+        for (int i = tid; i < 3 * 9 * (CO_CH / 4); i += CO_T * CO_T) {
+            const int q = i % (CO_CH / 4), ot = i / (CO_CH / 4);      // ot = o * 9 + tap
+            *reinterpret_cast<float4 *>(wsm + ot * CO_CH + 4 * q) =
+                *reinterpret_cast<const float4 *>(a.w + (size_t)ot * a.C + c0 + 4 * q);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+            const float *px = tile + ((ty + tap / 3) * CO_HALO + tx + tap % 3) * CO_LD;
+#pragma unroll
+            for (int q = 0; q < CO_CH / 4; q++) {
+                const float4 v = *reinterpret_cast<const float4 *>(px + 4 * q);
+#pragma unroll
+                for (int o = 0; o < 3; o++) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(wsm + (o * 9 + tap) * CO_CH + 4 * q);
+                    acc[o] = fmaf(v.x, w4.x, acc[o]); acc[o] = fmaf(v.y, w4.y, acc[o]);
+                    acc[o] = fmaf(v.z, w4.z, acc[o]); acc[o] = fmaf(v.w, w4.w, acc[o]);
+                }
+            }
+        }
+    }
+    const int gy = y0 + ty, gx = x0 + tx;
+    if (gy < a.H && gx < a.W) {
+#pragma unroll
+        for (int o = 0; o < 3; o++) {
+            float v = acc[o] + a.bias[o];
+            v = fminf(fmaxf(v, a.clamp_lo), a.clamp_hi);
+            v = v * a.out_scale + a.out_shift;
+            a.out[(((size_t)b * 3 + o) * a.H + gy) * a.W + gx] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- AttnBlock core
 // out[b][i][:] = sum_j softmax_j(q_i . k_j * C^-0.5) v_j ; q,k,v,out NHWC [B][N][C].  grid (N/16, B), 256 threads.
 constexpr int AB_Q = 16;

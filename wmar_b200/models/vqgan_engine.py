@@ -121,7 +121,7 @@ class VQGANEngine:
             raise _lib.WmarError("VQGANEngine is CUDA only (no CPU fallback)")
         self.cfg = dict(cfg)
         self.max_batch = max_batch
-        self.precision = {"3xtf32": 0, "tf32": 1}[precision]
+        self.precision = {"3xtf32": 0, "tf32": 1, "bf16x3": 2, "bf16x3-dec": 3}[precision]
         self.handle = None
         self.latent = cfg["resolution"] // 2 ** (len(cfg["ch_mult"]) - 1)
         self.sync_weights(state)
