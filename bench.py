@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
-    ap.add_argument("--vqgan-precision", choices=["3xtf32", "tf32", "bf16x3", "bf16x3-dec"], default="3xtf32")
+    ap.add_argument("--vqgan-precision", choices=["3xtf32", "tf32", "bf16x3", "bf16x3-dec"], default="bf16x3")
     ap.add_argument("--rng", choices=["torch", "philox"], default="torch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
@@ -382,7 +382,7 @@ def run_taming(args, rank, world, dev, L, peaks):
     blk = generation_block(args, world, B, steps_tok, m, model._gpt.algorithmic_bytes(B, steps_tok), peaks,
                            "decode loop (256 token steps: skinny GEMMs + KV attention + fused sampler)",
                            "decode_loop_dram_bytes_per_launch")
-    blk.update({"metric": METRIC, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
+    blk.update({"metric": METRIC, "dtype": "f32 (transformer: 3xTF32 tensor-core products, fp32 accumulate; VQGAN 3x3 convs: " + args.vqgan_precision + ")",
                 "config": {"workload": "taming_cin_B16_wm_linear_h1_d2_g0.25" + ("_SMALL_INVALID" if args.small else ""),
                            "batch_per_gpu": B, "global_batch": B * world, "tokens_per_image": steps_tok,
                            "gpt": gpt_cfg, "watermark": WM_STRING, "gen_params": GEN_PARAMS,
@@ -528,7 +528,7 @@ def run_rar_xl(args, rank, world, dev, L, peaks):
     blk = generation_block(args, world, B, steps_tok, m, model._rar.algorithmic_bytes(B, steps_tok), peaks,
                            "RAR decode loop (256 guided passes over 16 rows: skinny GEMMs + KV attention + CFG / watermark / sampler)",
                            "rar_decode_loop_dram_bytes_per_launch")
-    blk.update({"metric": RAR_METRIC, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
+    blk.update({"metric": RAR_METRIC, "dtype": "f32 (transformer: 3xTF32 tensor-core products, fp32 accumulate; VQGAN 3x3 convs: " + args.vqgan_precision + ")",
                 "config": {"workload": "rar_xl_256_B8_cfg4_wm_linear_h1_d2_g0.25" + ("_SMALL_INVALID" if args.small else ""),
                            "batch_per_gpu": B, "global_batch": B * world, "tokens_per_image": steps_tok, "rar": cfg,
                            "guidance_scale": 4.0, "watermark": WM_STRING, "vqgan_precision": args.vqgan_precision,
@@ -612,17 +612,19 @@ def run_detect(args, rank, world, dev, L, peaks):
     ach = fl * args.steps / (t_dev_ms * 1e-3) / 1e12
     blk = {"metric": DETECT_METRIC, "value": n_img / (t_dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
+           "vs_baseline": None, "dtype": "f32 (VQGAN convs: " + args.vqgan_precision + " tensor-core products, fp32 accumulate)", "data": "synthetic",
            "config": {"workload": "detect_only_taming_encode_256_B16x8", "batch_per_gpu": B, "batches_per_step": n_batches,
                       "watermark": WM_STRING, "vqgan_precision": args.vqgan_precision, "parallelism": f"replicas x{world}",
                       "l2": "8 x 12.6 MB of images per step + activations larger than L2 between batches"},
            "e2e": {"value": n_img / (t_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * n_batches * 3 * 256 * 256 * 4,
                    "d2h_bytes_per_step": stat_pin.numel() * 8, "ms_per_step": t_e2e_ms / args.steps},
            "gpu_launches": int(launches),
-           "roofline": {"bound": "tensor", "kernel": "VQGAN encoder conv stack (tcgen05 3xTF32 implicit GEMM) + codebook arg-min",
+           "roofline": {"bound": "tensor", "kernel": "VQGAN encoder conv stack (persistent tcgen05 implicit GEMM, " + args.vqgan_precision + ") + codebook arg-min",
                         "achieved": ach, "peak": pk, "peak_source": "measured bf16_tflops_sustained" if peaks else "fallback",
                         "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
-                        "note": "useful fp32-equivalent FLOPs; every product is 3 TF32 MMAs, whose own ceiling is 1/6 of the bf16 peak"},
+                        "note": ("useful fp32-equivalent FLOPs; every product is 3 bf16 MMAs (two-term split), whose own ceiling is 1/3 of the bf16 peak"
+                                 if args.vqgan_precision.startswith("bf16x3") else
+                                 "useful fp32-equivalent FLOPs; every product is 3 TF32 MMAs, whose own ceiling is 1/6 of the bf16 peak")},
            "detector": {"p_mean": float(torch.cat([s_["pvalue"] for s_ in sts]).mean())}, "clocks": clk}
     del m, wm
     torch.cuda.empty_cache()

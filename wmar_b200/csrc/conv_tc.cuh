@@ -38,6 +38,8 @@ struct ConvTcArgs {
     int H, W, Cin, Cout;     // Cin = padded input channels (multiple of 32), Cout = real output channels (multiple of 128)
     int bw, bh;              // pixel tile: bw x bh = 128
     int tiles_x, tiles_y;    // W / bw, H / bh
+    int stride, pad;         // bf16 kernel only: 1 / 1 (same conv) or 2 / 0 (downsample conv: pad (0,1,0,1) = TMA zero fill
+                             // past the right / bottom edge, model.py:69-72); H, W are the OUTPUT dims
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap *m, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -308,8 +310,9 @@ conv3x3_tc_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                     mbar_wait(s_empty(s), ((g / CB_NS) & 1) ^ 1);
                     mbar_arrive_expect_tx(s_full(s), CB_STAGE_BYTES);
                     const uint32_t dst = smem_base + s * CB_STAGE_BYTES;
-                    tma_load_4d(dst, &mapA, ci0, x0 + kx - 1, y0 + ky - 1, b, s_full(s));           // zero fill = padding
-                    tma_load_4d(dst + CT_TILE_BYTES, &mapA, ci0 + 32, x0 + kx - 1, y0 + ky - 1, b, s_full(s));
+                    const int sx = a.stride * x0 + kx - a.pad, sy = a.stride * y0 + ky - a.pad;
+                    tma_load_4d(dst, &mapA, ci0, sx, sy, b, s_full(s));                                // zero fill = padding
+                    tma_load_4d(dst + CT_TILE_BYTES, &mapA, ci0 + 32, sx, sy, b, s_full(s));
                     tma_load_2d(dst + 2 * CT_TILE_BYTES, &mapW1, tap * a.Cin + ci0, n0, s_full(s), L2_EVICT_LAST);
                     tma_load_2d(dst + 3 * CT_TILE_BYTES, &mapW2, tap * a.Cin + ci0, n0, s_full(s), L2_EVICT_LAST);
                 }

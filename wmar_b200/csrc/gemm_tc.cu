@@ -124,14 +124,16 @@ int tc_weight_map_bf16(const void *W, int N, int K, CUtensorMap *out) {
     return WMAR_OK;
 }
 
-// NHWC fp32 activations [B][H][W][C] -> 4-D map (C innermost), box [1][bh][bw][32], 128-byte swizzle, zero fill outside
-int tc_nhwc_map(const float *base, int B, int H, int W, int C, int bw, int bh, CUtensorMap *out) {
+// NHWC fp32 activations [B][H][W][C] -> 4-D map (C innermost), box [1][bh][bw][32], 128-byte swizzle, zero fill outside.
+// estride = 2: every other pixel in x and y (the stride-2 convs): the box spans 2 bw x 2 bh source pixels, of which the
+// TMA unit loads ceil(box / stride) = bw x bh.
+int tc_nhwc_map(const float *base, int B, int H, int W, int C, int bw, int bh, CUtensorMap *out, int estride) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(WMAR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver%s%s");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -38,6 +38,7 @@ struct Op {
     // gn (conv: gamma / beta of the GroupNorm fused into the decoder-tail kernel, fused_gn = 1)
     const float *gamma, *beta;
     int swish, H, W, C;
+    int direct_in;    // conv: encoder conv_in on conv_in3_kernel, straight from the caller's NCHW image
     int stats_only;   // gn: only the statistics pass runs, the consumer (conv_out3_kernel) normalises while staging
     int fused_gn;
     // attn: q,k,v buffers
@@ -65,6 +66,7 @@ struct wmar_vqgan {
     double2 *gn_partial;
     double flops_enc, flops_dec;
     int enc_out_buf, latent;  // buffer holding the encoder output (pre-quant z), latent side
+    const float *enc_images = nullptr;   // the caller's NCHW images of the running encode call (conv_in3_kernel reads them)
 };
 
 namespace {
@@ -166,6 +168,8 @@ int build_plans(wmar_vqgan *v, const void *const *tab, int n) {
         int t = b.free_buf({b.x});
         b.conv(b.x, t, -1, c.ch, 3, 1, 1, 0);
         b.flops -= 2.0 * c.resolution * c.resolution * (double)c.ch * 9.0 * 29.0;  // padded input channels are zeros
+        const char *e = getenv("WMAR_CONVIN");
+        if (!(e && e[0] == 'v') && c.ch % 128 == 0) b.ops->back().direct_in = 1;
         b.x = t;
     }
     int res = c.resolution;
@@ -270,6 +274,15 @@ bool conv_tc_eligible(const Op &o) {
     return 128 % Wi == 0 && Hi % (128 / Wi) == 0 && 128 / Wi <= 256;
 }
 
+// stride-2 downsample convs (3x3, pad (0,1,0,1), model.py:57-76) on the bf16x3 tcgen05 kernel: TMA element stride 2
+bool conv_tc_s2_eligible(const Op &o) {
+    if (o.ks != 3 || o.stride != 2 || o.pad != 0 || o.final_out || o.up) return false;
+    if (o.C != o.Cin || o.Cin % 64 != 0 || o.Cout % 128 != 0 || o.Cout != o.Cout_pad) return false;
+    if (o.Hs != 2 * o.Ho || o.Ws != 2 * o.Wo || o.Wo < 8) return false;
+    if (o.Wo >= 128) return o.Wo % 128 == 0;
+    return 128 % o.Wo == 0 && o.Ho % (128 / o.Wo) == 0;
+}
+
 // nearest x2 (taming model.py:39-54 Upsample: F.interpolate(scale_factor=2, mode="nearest")), NHWC, 16-byte vectors
 __global__ void upsample2x_nhwc_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int B, int H, int W, int C4) {
     const size_t n = (size_t)B * 2 * H * 2 * W * C4;
@@ -306,7 +319,8 @@ int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
     a.tiles_x = o.Wo / a.bw; a.tiles_y = o.Ho / a.bh;
     CUtensorMap mA, mWh, mWl;
     int rc;
-    if ((rc = tc_nhwc_map(src, B, o.Ho, o.Wo, o.Cin, a.bw, a.bh, &mA))) return rc;
+    a.stride = o.stride; a.pad = o.stride == 2 ? 0 : 1;
+    if ((rc = tc_nhwc_map(src, B, o.stride * o.Ho, o.stride * o.Wo, o.Cin, a.bw, a.bh, &mA, o.stride))) return rc;
     if (o.wb1 != nullptr) {
         // bf16x3: persistent kernel, one CTA per SM walking the (pixel tile, 128-channel block) list
         static bool configured_b = false;
@@ -338,6 +352,17 @@ int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
 int gn_chunks(int HW, int C);
 
 int run_conv(const wmar_vqgan *v, const Op &o, int B, float *final_out, cudaStream_t s) {
+    if (o.direct_in) {
+        ConvInArgs a{};
+        a.img = v->enc_images; a.w = o.w; a.bias = o.b; a.out = v->buf[o.dst];
+        a.H = o.Ho; a.W = o.Wo; a.Cout = o.Cout; a.Cin_pad = o.Cin;
+        a.scale = v->cfg.family == 1 ? 0.5f : 1.f; a.shift = v->cfg.family == 1 ? 0.5f : 0.f;   // rar_wrapper.py:124
+        dim3 grid((unsigned)((o.Wo + CI_TW - 1) / CI_TW), (unsigned)((o.Ho + CI_TH - 1) / CI_TH), (unsigned)B);
+        const size_t smem = sizeof(float) * (27 * (size_t)o.Cout + 3 * (CI_TH + 2) * (CI_TW + 2));
+        conv_in3_kernel<<<grid, 256, smem, s>>>(a);
+        WMAR_LAUNCH_CHECK();
+        return WMAR_OK;
+    }
     if (o.wlo != nullptr) return run_conv_tc(v, o, B, s);
     if (o.fused_gn) {
         ConvOutArgs a{};
@@ -466,12 +491,13 @@ int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights
         for (auto *ops : {&v->enc, &v->dec})
             for (Op &o : *ops) {
                 o.wlo = nullptr;
-                if (!want_tc || o.kind != OP_CONV || !conv_tc_eligible(o)) continue;
+                const bool bf = cfg->precision == 2 || (cfg->precision == 3 && ops == &v->dec);
+                const bool s2 = bf && o.kind == OP_CONV && conv_tc_s2_eligible(o);
+                if (!want_tc || o.kind != OP_CONV || o.direct_in || !(conv_tc_eligible(o) || s2)) continue;
                 const size_t nw = (size_t)o.Cout_pad * 9 * o.Cin;
-                WMAR_CUDA_CHECK(cudaMalloc(&o.wlo, sizeof(float) * nw));
+                WMAR_CUDA_CHECK(cudaMalloc(&o.wlo, sizeof(float) * nw));   // (also the "tcgen05 path" marker of run_conv)
                 conv_tc_wlo_kernel<<<1024, 256>>>(o.w, o.wlo, nw);
                 WMAR_LAUNCH_CHECK();
-                const bool bf = cfg->precision == 2 || (cfg->precision == 3 && ops == &v->dec);
                 if (bf && o.Cin % 64 == 0) {
                     WMAR_CUDA_CHECK(cudaMalloc(&o.wb1, sizeof(uint16_t) * nw));
                     WMAR_CUDA_CHECK(cudaMalloc(&o.wb2, sizeof(uint16_t) * nw));
@@ -520,8 +546,11 @@ int wmar_vqgan_encode(wmar_vqgan *v, const float *d_images, int64_t B, int64_t *
     size_t total = (size_t)B * R * R * 32;
     // RAR feeds (x+1)/2 to its encoder (rar_wrapper.py:124)
     const float scale = v->cfg.family == 1 ? 0.5f : 1.f, shift = v->cfg.family == 1 ? 0.5f : 0.f;
-    nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_images, v->buf[0], (int)B, R * R, 32, scale, shift);
-    WMAR_LAUNCH_CHECK();
+    v->enc_images = d_images;
+    if (!v->enc.front().direct_in) {
+        nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_images, v->buf[0], (int)B, R * R, 32, scale, shift);
+        WMAR_LAUNCH_CHECK();
+    }
     int rc = run_ops(v, v->enc, (int)B, nullptr, s);
     if (rc) return rc;
     // nearest codebook entry: dots = z . e^T (always 3xTF32), d = (|z|^2 + |e|^2) - 2 dots, first arg-min
