@@ -34,14 +34,28 @@ static unsigned long long *gemm_trace_for(int pro, int epi) {
     return (g_gemm_trace_kind == pro * 10 + epi) ? g_gemm_trace : nullptr;
 }
 
+// WMAR_GEMM_LOAD=cpasync keeps the per-lane cp.async weight ring; default: TMA boxes (one instruction per warp iteration)
+static bool gemm_tma() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("WMAR_GEMM_LOAD"); on = (e && e[0] == 'c') ? 0 : (tc_available() ? 1 : 0); }
+    return on == 1;
+}
+
 template <int PRO, int EPI>
 static int launch_t(const GemmArgs &a_in, cudaStream_t stream) {
     GemmArgs a = a_in;
     a.trace = gemm_trace_for(PRO, EPI);
     static bool configured = false;
     if (!configured) {
-        WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO, EPI, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO, EPI, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         configured = true;
+    }
+    const bool tma = gemm_tma() && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0 && a.K % 4 == 0;
+    CUtensorMap wmap{};
+    if (tma) {
+        int rc = tc_weight_map_skinny(a.W, a.N, a.K, &wmap);
+        if (rc) return rc;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(a.N / GEMM_NT), (unsigned)a.splits, 1);
@@ -53,7 +67,8 @@ static int launch_t(const GemmArgs &a_in, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = v0_pdl() ? 1 : 0;
-    WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<PRO, EPI>, a));
+    if (tma) WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<PRO, EPI, 0, true>, a, wmap));
+    else WMAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<PRO, EPI, 0, false>, a, wmap));
     g_launches.fetch_add(1);
     return WMAR_OK;
 }
@@ -170,8 +185,9 @@ extern "C" int wmar_skinny_gemm(const float *d_x, const float *d_w, const float 
         dim3 grid((unsigned)(a.N / GEMM_NT), (unsigned)a.splits);
         WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO_NONE, EPI_STORE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         WMAR_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<PRO_NONE, EPI_STORE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-        if (g_probe_mode == 1) skinny_gemm_kernel<PRO_NONE, EPI_STORE, 1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, as_stream(stream)>>>(a);
-        else skinny_gemm_kernel<PRO_NONE, EPI_STORE, 2><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, as_stream(stream)>>>(a);
+        CUtensorMap nomap{};
+        if (g_probe_mode == 1) skinny_gemm_kernel<PRO_NONE, EPI_STORE, 1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, as_stream(stream)>>>(a, nomap);
+        else skinny_gemm_kernel<PRO_NONE, EPI_STORE, 2><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, as_stream(stream)>>>(a, nomap);
         WMAR_LAUNCH_CHECK();
         return WMAR_OK;
     }

@@ -18,6 +18,7 @@
 //     GEMM's epilogue emitted as (mean, M2) partials per 64-column tile, combined with Chan's formula.
 #pragma once
 #include "common.cuh"
+#include "tc05.cuh"
 
 namespace wmar {
 
@@ -159,9 +160,14 @@ __device__ __forceinline__ void combine_row_stats(const float2 *__restrict__ sta
     }
 }
 
-template <int PRO, int EPI, int MODE = 0>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a) {
-    extern __shared__ __align__(16) uint8_t gemm_smem[];
+// TMA = true: the weight ring is filled by the TMA unit instead of per-lane cp.async -- one elected lane per warp issues ONE
+// cp.async.bulk.tensor.2d per iteration (box 16 k x 64 rows of W = 4 KB, no swizzle), which lands in the warp's ring stage
+// in exactly the [n8 tile][lane][16 B] order the lanes read back (row r of the box = tile r / 8, g = r % 8; its 64 bytes =
+// the four t pieces), completion on a per-(warp, stage) mbarrier.  No cross-warp synchronisation either way.
+template <int PRO, int EPI, int MODE = 0, bool TMA = false>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a, const __grid_constant__ CUtensorMap wmap) {
+    extern __shared__ __align__(128) uint8_t gemm_smem[];
+    __shared__ __align__(8) unsigned long long ring_bar[GEMM_WARPS * GEMM_STAGES];
     float *red = reinterpret_cast<float *>(gemm_smem);   // cross-warp reduction buffer: aliases the drained ring
     __shared__ float2 row_stats[GEMM_M];
     __shared__ int s_is_last;
@@ -181,7 +187,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
     // producer kernel.  One commit group per iteration (empty groups keep the count constant).
     const float *wbase = a.W + (size_t)(n0 + g) * a.K + kw0 + 4 * t;
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(gemm_smem) + (uint32_t)(warp * GEMM_STAGES * GEMM_STAGE_BYTES) + (uint32_t)(lane * 16);
+    const uint32_t bar0 = tc05::smem_u32(ring_bar) + (uint32_t)(warp * GEMM_STAGES * 8);
+    if (TMA) {
+        if (lane == 0) {
+            if (warp == 0) tc05::tma_prefetch_desc(&wmap);
+#pragma unroll
+            for (int s0 = 0; s0 < GEMM_STAGES; s0++) tc05::mbar_init(bar0 + 8u * s0, 1);
+            tc05::mbar_fence_init();
+        }
+        __syncwarp();
+    }
     auto issue = [&](int it) {
+        if (TMA) {
+            if (it < iters && lane == 0) {
+                const uint32_t st = (uint32_t)(it % GEMM_STAGES);
+                tc05::mbar_arrive_expect_tx(bar0 + 8u * st, GEMM_STAGE_BYTES);
+                tc05::tma_load_2d(ring - (uint32_t)(lane * 16) + st * GEMM_STAGE_BYTES, &wmap, kw0 + it * KSTEP, n0, bar0 + 8u * st,
+                                  tc05::L2_EVICT_FIRST);
+            }
+            return;
+        }
         if (it < iters) {
             const uint32_t dst = ring + (uint32_t)((it % GEMM_STAGES) * GEMM_STAGE_BYTES);
 #pragma unroll
@@ -259,13 +284,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
             for (int e = 0; e < 4; e++) split_tf32(xs[r][e], xh[r][e], xl[r][e]);
         // this iteration's weights have landed (at most STAGES-1 newer groups may still be in flight); pull them into
         // registers and hand the stage to iteration it + STAGES
-        gm_cp_wait<GEMM_STAGES - 1>();
+        if (TMA) tc05::mbar_wait(bar0 + 8u * (uint32_t)(it % GEMM_STAGES), (uint32_t)(it / GEMM_STAGES) & 1u);
+        else gm_cp_wait<GEMM_STAGES - 1>();
         float4 wcur[GEMM_TILES];
         {
             const uint8_t *src = gemm_smem + (warp * GEMM_STAGES + (it % GEMM_STAGES)) * GEMM_STAGE_BYTES + lane * 16;
 #pragma unroll
             for (int j = 0; j < GEMM_TILES; j++) wcur[j] = *reinterpret_cast<const float4 *>(src + j * 512);
         }
+        if (TMA) __syncwarp();   // every lane has read the stage before the TMA unit overwrites it
         issue(it + GEMM_STAGES);
         if (it < 4) GM_TRACE(3 + it);
 #pragma unroll
@@ -293,7 +320,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
         }
     }
     GM_TRACE(7);
-    gm_cp_wait<0>();
+    if (!TMA) gm_cp_wait<0>();
     __syncthreads();   // every warp is done with its ring: the reduction buffer below aliases it
 
     // ---- cross-warp reduction (fixed order) ----

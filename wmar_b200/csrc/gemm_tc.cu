@@ -102,6 +102,28 @@ void tc_gemm_set_dbg(int bits) { g_tc_dbg = bits; }
 
 int tc_weight_map(const float *W, int N, int K, CUtensorMap *out) { return weight_map(W, N, K, out); }
 
+// W[N][K] fp32 row-major -> 2-D map (K innermost), box 16 x 64, no swizzle: one warp iteration of skinny_gemm_kernel
+int tc_weight_map_skinny(const float *W, int N, int K, CUtensorMap *out) {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    MapKey key{W, -N, K};                       // negative N: skinny-GEMM entry of the shared cache
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return WMAR_OK; }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(WMAR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver%s%s");
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint32_t box[2] = {16, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(W), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(WMAR_ERR_CUDA, "cuTensorMapEncodeTiled (skinny GEMM weights) failed%s%s");
+    g_maps.emplace(key, m);
+    *out = m;
+    return WMAR_OK;
+}
+
 // W[N][K] bf16 row-major -> 2-D map (K innermost), box 64 x 128 (128-byte rows), 128-byte swizzle (conv_tc.cuh, bf16x3)
 int tc_weight_map_bf16(const void *W, int N, int K, CUtensorMap *out) {
     std::lock_guard<std::mutex> lk(g_map_mu);

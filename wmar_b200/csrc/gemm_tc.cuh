@@ -326,6 +326,7 @@ int tc_pick_splits(int N, int K, int n_sms);
 int launch_tc_gemm(int pro, int epi, const GemmArgs &a, cudaStream_t stream);
 int tc_weight_map(const float *W, int N, int K, CUtensorMap *out);   // cached TMA descriptor of W[N][K]
 bool tc_available();                                                // driver exposes cuTensorMapEncodeTiled
+int tc_weight_map_skinny(const float *W, int N, int K, CUtensorMap *out);   // fp32 W[N][K], box 16 x 64, no swizzle (gemm.cuh, TMA ring)
 int tc_weight_map_bf16(const void *W, int N, int K, CUtensorMap *out);   // bf16 W[N][K], box 64 x 128 (conv_tc.cuh, bf16x3)
 int tc_nhwc_map(const float *base, int B, int H, int W, int C, int bw, int bh, CUtensorMap *out, int estride = 1);   // conv_tc.cuh A operand
 
