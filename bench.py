@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--lanes", type=int, default=2, help="extra block: this many batches of 16 on concurrent engine lanes (1 = skip)")
     ap.add_argument("--vqgan-precision", choices=["3xtf32", "tf32", "bf16x3", "bf16x3-dec"], default="bf16x3")
     ap.add_argument("--rng", choices=["torch", "philox"], default="torch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -389,6 +390,22 @@ def run_taming(args, rank, world, dev, L, peaks):
                            "vqgan_precision": args.vqgan_precision, "rng": args.rng, "parallelism": f"replicas x{world}",
                            "step_path": os.environ.get("WMAR_STEP", "default"),
                            "l2": "inputs larger than L2 (5.5 GB of weights streamed per token step)"}})
+    if args.lanes > 1:
+        # the same wrapper call with 2 x B conditionings: two batches of B run concurrently on two engine lanes (own KV
+        # cache / scratch / step graph, shared weights; taming_wrapper.py sample()).  A step here = 2 x B images.
+        model.lanes = args.lanes
+        cond2 = [CLASSES[(rank * B + i) % len(CLASSES)] for i in range(args.lanes * B)]
+        m2 = measure_generation(args, world, dev, model, wm, cond2, GEN_PARAMS, steps_tok, L)
+        b2 = generation_block(args, world, args.lanes * B, steps_tok, m2, args.lanes * model._gpt.algorithmic_bytes(B, steps_tok), peaks,
+                              f"{args.lanes} concurrent decode loops (each 256 token steps at {B} rows; every loop streams the weights itself)",
+                              None)
+        b2.update({"metric": METRIC.replace("batch 16/GPU", f"{args.lanes} concurrent batches of 16/GPU"), "dtype": blk["dtype"],
+                   "config": dict(blk["config"], workload=f"taming_cin_{args.lanes}xB16_concurrent_lanes_wm_linear_h1_d2_g0.25",
+                                  batch_per_gpu=args.lanes * B, global_batch=args.lanes * B * world, lanes=args.lanes,
+                                  note="NOT the headline configuration: the wrapper's sample() is given 2 x 16 conditionings and "
+                                       "runs the two batches of 16 on two engine lanes / CUDA streams; ids identical to the "
+                                       "sequential chunk loop (tests/test_gpu_watermark.py)")})
+        blk["_lanes_block"] = b2
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         gs = {k[len("transformer."):]: v.cpu() for k, v in state.items() if k.startswith("transformer.")}
         vs = {k[len("first_stage_model."):]: v.cpu() for k, v in state.items() if k.startswith("first_stage_model.")}
@@ -534,6 +551,18 @@ def run_rar_xl(args, rank, world, dev, L, peaks):
                            "guidance_scale": 4.0, "watermark": WM_STRING, "vqgan_precision": args.vqgan_precision,
                            "rng": args.rng, "parallelism": f"replicas x{world}",
                            "l2": "inputs larger than L2 (weights streamed per pass)"}})
+    if args.lanes > 1:
+        model.lanes = args.lanes     # same wrapper call with lanes x 8 conditionings: concurrent engine lanes (see run_taming)
+        cond2 = [RAR_CLASSES[(rank * B + i) % len(RAR_CLASSES)] for i in range(args.lanes * B)]
+        m2 = measure_generation(args, world, dev, model, wm, cond2, None, steps_tok, L)
+        b2 = generation_block(args, world, args.lanes * B, steps_tok, m2, args.lanes * model._rar.algorithmic_bytes(B, steps_tok), peaks,
+                              f"{args.lanes} concurrent RAR decode loops (each 256 guided passes over 16 rows; every loop streams the weights itself)",
+                              None)
+        b2.update({"metric": RAR_METRIC.replace("batch 8/GPU", f"{args.lanes} concurrent batches of 8/GPU"), "dtype": blk["dtype"],
+                   "config": dict(blk["config"], workload=f"rar_xl_256_{args.lanes}xB8_concurrent_lanes_cfg4_wm_linear_h1_d2_g0.25",
+                                  batch_per_gpu=args.lanes * B, global_batch=args.lanes * B * world, lanes=args.lanes,
+                                  note="NOT configuration 3 itself: lanes x 8 images per GPU per step on concurrent engine lanes")})
+        blk["lanes_block"] = b2
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         blk["cpu_baseline"] = rar_cpu_reference_throughput({k: v.cpu() for k, v in state.items()},
                                                            {k: v.cpu() for k, v in tstate.items()}, cfg, B,
@@ -648,6 +677,8 @@ def run_ours(args, rank, local_rank, world):
     if args.workload == "all":
         line = run_taming(args, rank, world, dev, L, peaks)
         extra = {}
+        if "_lanes_block" in line:
+            extra["taming_concurrent_lanes"] = line.pop("_lanes_block")
         for name, key in (("rar_xl", "rar_xl"), ("detect", "detect_only")):
             try:
                 extra[key] = runners[name](args, rank, world, dev, L, peaks)
@@ -658,6 +689,8 @@ def run_ours(args, rank, local_rank, world):
         line["extra_workloads"] = extra
     else:
         line = runners[args.workload](args, rank, world, dev, L, peaks)
+        if "_lanes_block" in line:
+            line["extra_workloads"] = {"taming_concurrent_lanes": line.pop("_lanes_block")}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -259,3 +259,60 @@ def test_wrapper_sampling_equals_torch_buffer_mode():
         torch.manual_seed(12)
         out[rng] = m.sample([1, 9, 232, 340, 975], None, apply_watermark=False).cpu()
     assert torch.equal(out["torch"], out["torch_buffer"])
+
+
+def test_wrapper_lanes_equal_sequential_chunk_loop():
+    """TamingARMMWrapper.sample with more conditionings than max_batch: chunk i runs on engine lane i % lanes (own KV
+    cache / scratch / step graph, shared weights) on that lane's CUDA stream.  The codes must equal the sequential chunk
+    loop (lanes=1) bit for bit -- sampled (torch's Philox stream, offsets assigned per chunk in order) and greedy -- on
+    repeated calls (lanes are reused), and torch's generator must end in the same state."""
+    from oracle import gpt as ogpt
+    from oracle import vqgan as ov
+    from wmar_b200.models import TamingARMMWrapper
+    from wmar_b200.watermarking import create_watermarker_from_string
+    V, steps = 16384, 64
+    gpt_cfg = dict(vocab_size=V, block_size=steps, n_layer=2, n_head=4, n_embd=256)
+    dd = dict(ov.TAMING_CFG, ch=128, ch_mult=(1, 2), resolution=16, attn_resolutions=(8,))
+    gw = ogpt.synthetic_gpt_weights(V, steps, 2, 4, 256, seed=7)
+    vw = ov.synthetic_taming_vqgan_weights(dd, seed=8)
+    state = {"transformer." + k: v for k, v in gw.items()}
+    state.update({"first_stage_model." + k: v for k, v in vw.items()})
+    gp = {"temperature": 1.0, "top_k": 250, "top_p": 0.92}
+    conds = [1, 9, 232, 975, 3, 4, 77, 500, 640, 12]                    # 3 chunks of max_batch = 4 (4 + 4 + 2 rows)
+    res = {}
+    for lanes in (1, 2, 3):
+        m = TamingARMMWrapper(state_dict=state, gpt_cfg=gpt_cfg, dd_cfg=dd, device="cuda", max_batch=4, lanes=lanes)
+        wm = create_watermarker_from_string(m.get_vq(), V, "linear-stratifiedrand-h=1-d=2.0-g=0.25", "cuda")
+        m.set_watermarker(wm)
+        torch.manual_seed(21)
+        a = m.sample(conds, gp, apply_watermark=True)
+        b = m.sample(conds, gp, apply_watermark=True)                   # second call: lanes reused, generator advanced
+        g = m.sample(conds, gp, apply_watermark=False, greedy=True)
+        img = m.codes_to_images(a)                                      # 10 rows > max_batch: chunked tokenizer calls
+        back = m.images_to_codes(img)
+        res[lanes] = (a.cpu(), b.cpu(), g.cpu(), torch.rand(4, device="cuda").cpu(), back.cpu())
+        assert img.shape == (10, 3, 16, 16) and back.shape == a.shape
+    for lanes in (2, 3):
+        for x, y in zip(res[1], res[lanes]):
+            assert torch.equal(x, y), lanes
+    assert not torch.equal(res[1][0], res[1][1])
+
+
+def test_rar_wrapper_lanes_equal_sequential_chunk_loop():
+    """RarARMMWrapper: same property as the Taming wrapper's lanes (chunks of max_batch on concurrent engine lanes ==
+    the sequential chunk loop, bit for bit, including the torch.rand_like draw RAR makes per chunk)."""
+    from wmar_b200.models import RarARMMWrapper
+    from wmar_b200.watermarking import create_watermarker_from_string
+    res = {}
+    conds = [1, 9, 232, 340, 975, 17, 600, 3, 44]                       # 3 chunks of max_batch = 4 (4 + 4 + 1 rows)
+    for lanes in (1, 2):
+        m = RarARMMWrapper(rar_cfg=dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512),
+                           max_batch=4, lanes=lanes)
+        wm = create_watermarker_from_string(m.get_vq(), m.get_total_vocab_size(), "linear-stratifiedrand-h=1-d=2.0-g=0.25", "cuda")
+        m.set_watermarker(wm)
+        torch.manual_seed(12)
+        a = m.sample(conds, None, apply_watermark=True)
+        b = m.sample(conds, None, apply_watermark=False, greedy=True)
+        res[lanes] = (a.cpu(), b.cpu(), torch.rand(4, device="cuda").cpu())
+    for x, y in zip(res[1], res[2]):
+        assert torch.equal(x, y)

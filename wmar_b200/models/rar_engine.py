@@ -50,6 +50,21 @@ class RAREngine:
         t += [dev("adaln_before_head.adaLN_modulation.1.weight"), dev("adaln_before_head.adaLN_modulation.1.bias"),
               dev("lm_head.weight"), dev("lm_head.bias")]
         self._tensors = t
+        self._create()
+
+    def clone_lane(self):
+        """A second engine over the SAME weight tensors with its own KV cache / scratch / graphs: an independent lane
+        whose generations run concurrently with this one's on another CUDA stream (gpt_engine.TamingGPTEngine.clone_lane)."""
+        lane = object.__new__(type(self))
+        for k in ("device", "n_layer", "n_head", "codebook_size", "n_classes", "image_seq_len", "max_batch", "hidden", "mlp"):
+            setattr(lane, k, getattr(self, k))
+        lane.handle = None
+        lane._tensors = self._tensors
+        lane._create()
+        return lane
+
+    def _create(self):
+        t = self._tensors
         L = _lib.lib()
         if self.handle is not None:
             L.wmar_rar_destroy(self.handle)
@@ -71,7 +86,7 @@ class RAREngine:
 
     @torch.no_grad()
     def sample(self, cond, steps=None, guidance_scale=4.0, temperature=1.0, watermarker=None, noise=None, greedy=False,
-               seed=0, return_logits=False, torch_stream=None):
+               seed=0, return_logits=False, torch_stream=None, defer_check=False):
         """cond int64[B] class ids -> ids int64[B, steps]; noise fp32[steps,B,V] ~ Exp(1) or None (in-kernel Philox)."""
         steps = steps or self.image_seq_len
         cond = torch.as_tensor(cond, dtype=torch.long, device=self.device).reshape(-1).contiguous()
@@ -93,7 +108,8 @@ class RAREngine:
                                                   ctypes.byref(sp), _lib.ptr(cond), B, steps, float(guidance_scale),
                                                   _lib.ptr(noise), _lib.ptr(out), _lib.ptr(logits),
                                                   _lib.current_stream()))
-            _lib.check_device_flag()   # raises on an out-of-range context sum / top-p overflow (device-side checks)
+            if not defer_check:        # (lanes: the caller checks once after joining the streams)
+                _lib.check_device_flag()   # raises on an out-of-range context sum / top-p overflow (device-side checks)
         self._keepalive = (cond, noise)
         return (out, logits) if return_logits else out
 

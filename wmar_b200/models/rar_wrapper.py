@@ -20,7 +20,7 @@ ASSETS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 
 class RarARMMWrapper(AutoregressiveMultimodalModelWrapper):
     def __init__(self, modelpath=None, rar_size="rar_xl", *, state_dict=None, tokenizer_state_dict=None, rar_cfg=None,
-                 vq_cfg=None, device="cuda", max_batch=8, vqgan_precision="bf16x3", seed=0, alive_ids_path=None,
+                 vq_cfg=None, device="cuda", max_batch=8, vqgan_precision="bf16x3", seed=0, alive_ids_path=None, lanes=2,
                  rng="torch"):
         """modelpath: directory holding ``{rar_size}.bin`` and ``maskgit-vqgan-imagenet-f16-256.bin`` (the files the
         reference downloads, rar_wrapper.py:27-34); None -> seeded random-init weights at the ``rar_size`` shapes."""
@@ -56,6 +56,8 @@ class RarARMMWrapper(AutoregressiveMultimodalModelWrapper):
         self.dim_z = vq_cfg["z_channels"]
         self._rar = None
         self._vqgan = None
+        self.lanes = max(1, int(lanes))
+        self._lane_engines, self._lane_streams = [], []
         self._step_seed = seed
         self.sync_weights()
 
@@ -77,6 +79,7 @@ class RarARMMWrapper(AutoregressiveMultimodalModelWrapper):
                                   max_batch=min(self.max_batch, 8))
         else:
             self._rar.sync_weights(rstate)
+        self._lane_engines, self._lane_streams = [], []   # lanes borrow the engine's tensors: rebuilt on demand
         v = self.vq_cfg
         ecfg = dict(family=1, ch=v["hidden_channels"], ch_mult=tuple(v["channel_mult"]),
                     num_res_blocks=v["num_res_blocks"], attn_resolution=0, resolution=v["resolution"],
@@ -88,6 +91,15 @@ class RarARMMWrapper(AutoregressiveMultimodalModelWrapper):
         else:
             self._vqgan.sync_weights(tstate)
 
+    def _lane(self, k):
+        """Engine + stream of lane k (lane 0 = the wrapper's own engine on the caller's stream); see TamingARMMWrapper."""
+        if k == 0:
+            return self._rar, None
+        while len(self._lane_engines) < k:
+            self._lane_engines.append(self._rar.clone_lane())
+            self._lane_streams.append(torch.cuda.Stream(device=self.device))
+        return self._lane_engines[k - 1], self._lane_streams[k - 1]
+
     # conditioning: list of size [b] of class indices.  Returns detached codes [b, 256]  (rar_wrapper.py:89-107)
     def sample(self, conditioning, gen_params=None, apply_watermark=False, greedy=False):
         cond = torch.as_tensor(conditioning, device=self.device).view(-1).long()
@@ -96,7 +108,17 @@ class RarARMMWrapper(AutoregressiveMultimodalModelWrapper):
         V = self.rar_cfg["codebook_size"]
         out = []
         mb = self._rar.max_batch
-        for i in range(0, cond.numel(), mb):
+        n_chunks = (cond.numel() + mb - 1) // mb
+        n_lanes = min(self.lanes, n_chunks)      # chunk i -> lane i % n_lanes, concurrently (weights shared)
+        if n_lanes - 1 > len(self._lane_engines):
+            # create the missing lanes BEFORE any work of this call is enqueued: engine creation zero-fills its buffers on
+            # the legacy default stream, which would queue behind lane 0's generation and land in the middle of lane 1's
+            self._lane(n_lanes - 1)
+            torch.cuda.synchronize(self.device)
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)                                # everything the caller enqueued before this call (cond, weights)
+        for ci, i in enumerate(range(0, cond.numel(), mb)):
             c = cond[i:i + mb]
             noise, stream = None, None
             if not greedy and self.rng in ("torch", "torch_buffer"):
@@ -107,20 +129,41 @@ class RarARMMWrapper(AutoregressiveMultimodalModelWrapper):
                 else:
                     noise = self._draw_noise(steps, c.numel(), V)
             self._step_seed += 1
-            out.append(self._rar.sample(c, steps, guidance_scale=4.0, temperature=1.0, watermarker=wm, noise=noise,
-                                        greedy=greedy, seed=self._step_seed, torch_stream=stream))
+            eng, lane_stream = self._lane(ci % n_lanes)
+            kw = dict(guidance_scale=4.0, temperature=1.0, watermarker=wm, noise=noise, greedy=greedy, seed=self._step_seed,
+                      torch_stream=stream)
+            if lane_stream is None:
+                out.append(eng.sample(c, steps, defer_check=n_lanes > 1, **kw))
+            else:
+                # NOT wait_stream(main): lane 0's generation was just enqueued there and the lanes must overlap it
+                if noise is not None:
+                    lane_stream.wait_stream(main)         # (legacy torch_buffer mode: the noise was drawn on `main`)
+                else:
+                    lane_stream.wait_event(ready)
+                with torch.cuda.stream(lane_stream):
+                    o = eng.sample(c, steps, defer_check=True, **kw)
+                o.record_stream(main)
+                out.append(o)
+        if n_lanes > 1:
+            for k in range(1, n_lanes):
+                main.wait_stream(self._lane_streams[k - 1])
+            _lib.check_device_flag()
         codes = out[0] if len(out) == 1 else torch.cat(out, dim=0)
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
         return codes
 
     def codes_to_images(self, codes):
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
-        images = self._vqgan.decode(codes)  # clamp(0,1) * 2 - 1 inside the kernel (rar_wrapper.py:114-116)
+        mb = self._vqgan.max_batch           # clamp(0,1) * 2 - 1 inside the kernel (rar_wrapper.py:114-116)
+        images = self._vqgan.decode(codes) if codes.shape[0] <= mb else torch.cat(
+            [self._vqgan.decode(codes[i:i + mb]) for i in range(0, codes.shape[0], mb)], dim=0)
         assert self.is_images_shaped(images), f"Images shape: {images.shape}"
         return images
 
     def images_to_codes(self, images):
         assert self.is_images_shaped(images), f"Images shape: {images.shape}"
-        codes = self._vqgan.encode(images)  # (x + 1) / 2 inside the kernel (rar_wrapper.py:124)
+        mb = self._vqgan.max_batch           # (x + 1) / 2 inside the kernel (rar_wrapper.py:124)
+        codes = self._vqgan.encode(images) if images.shape[0] <= mb else torch.cat(
+            [self._vqgan.encode(images[i:i + mb]) for i in range(0, images.shape[0], mb)], dim=0)
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
         return codes

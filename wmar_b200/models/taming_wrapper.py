@@ -38,12 +38,15 @@ def _load_net2net(modelpath):
 
 class TamingARMMWrapper(AutoregressiveMultimodalModelWrapper):
     def __init__(self, modelpath=None, *, state_dict=None, gpt_cfg=None, dd_cfg=None, device="cuda", max_batch=16,
-                 vqgan_precision="bf16x3", seed=0, alive_ids_path=None, rng="torch"):
+                 vqgan_precision="bf16x3", seed=0, alive_ids_path=None, rng="torch", lanes=2):
         """modelpath: directory of the reference's Taming download (README.md); None -> seeded random-init weights at
         ``gpt_cfg`` / ``dd_cfg`` shapes (default: the reference's cin_transformer shapes), or an explicit
         ``state_dict`` with Net2NetTransformer keys.  rng: "torch" draws torch.multinomial's own CUDA Philox stream inside
         the sampler kernel (same seeds -> same tokens as the reference, no noise buffer), "torch_buffer" lets torch pre-draw
-        that stream into a [steps, B, V] buffer (round 1), "philox" uses an independent in-kernel stream."""
+        that stream into a [steps, B, V] buffer (round 1), "philox" uses an independent in-kernel stream.
+        lanes: how many engine lanes (KV cache + scratch + step graph each, weights shared) ``sample`` may run concurrently
+        when it is given more than ``max_batch`` conditionings: chunk i goes to lane i % lanes on that lane's CUDA stream.
+        Results are identical to the sequential chunk loop (same per-chunk Philox offsets / seeds); lanes=1 is that loop."""
         super().__init__()
         self._device = torch.device(device)
         if self._device.type != "cuda":
@@ -72,6 +75,8 @@ class TamingARMMWrapper(AutoregressiveMultimodalModelWrapper):
         self.dim_z = dd_cfg["embed_dim"]
         self._gpt = None
         self._vqgan = None
+        self.lanes = max(1, int(lanes))
+        self._lane_engines, self._lane_streams = [], []
         self._step_seed = seed
         self.sync_weights()
 
@@ -94,6 +99,7 @@ class TamingARMMWrapper(AutoregressiveMultimodalModelWrapper):
                                         max_batch=self.max_batch)
         else:
             self._gpt.sync_weights(gstate)
+        self._lane_engines, self._lane_streams = [], []   # lanes borrow the engine's tensors: rebuilt on demand
         dd = self.dd_cfg
         ecfg = dict(family=0, ch=dd["ch"], ch_mult=tuple(dd["ch_mult"]), num_res_blocks=dd["num_res_blocks"],
                     attn_resolution=(dd["attn_resolutions"][0] if dd["attn_resolutions"] else 0),
@@ -105,13 +111,32 @@ class TamingARMMWrapper(AutoregressiveMultimodalModelWrapper):
         else:
             self._vqgan.sync_weights(vstate)
 
+    def _lane(self, k):
+        """Engine + stream of lane k (lane 0 = the wrapper's own engine on the caller's stream)."""
+        if k == 0:
+            return self._gpt, None
+        while len(self._lane_engines) < k:
+            self._lane_engines.append(self._gpt.clone_lane())
+            self._lane_streams.append(torch.cuda.Stream(device=self.device))
+        return self._lane_engines[k - 1], self._lane_streams[k - 1]
+
     # conditioning: list of size [b] (class ids).  Returns detached codes [b, codes_size**2]  (taming_wrapper.py:61-77)
     def sample(self, conditioning, gen_params, apply_watermark=False, greedy=False):
         cond = torch.as_tensor(conditioning, device=self.device).view(-1).long()
         steps = self.codes_size * self.codes_size
         wm = self.watermarker if apply_watermark else None
+        n_chunks = (cond.numel() + self.max_batch - 1) // self.max_batch
+        n_lanes = min(self.lanes, n_chunks)
+        if n_lanes - 1 > len(self._lane_engines):
+            # create the missing lanes BEFORE any work of this call is enqueued: engine creation zero-fills its buffers on
+            # the legacy default stream, which would queue behind lane 0's generation and land in the middle of lane 1's
+            self._lane(n_lanes - 1)
+            torch.cuda.synchronize(self.device)
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)                                # everything the caller enqueued before this call (cond, weights)
         out = []
-        for i in range(0, cond.numel(), self.max_batch):
+        for ci, i in enumerate(range(0, cond.numel(), self.max_batch)):
             c = cond[i:i + self.max_batch]
             noise, stream = None, None
             if not greedy and self.rng == "torch":            # torch.multinomial's draws, generated inside the sampler
@@ -119,21 +144,41 @@ class TamingARMMWrapper(AutoregressiveMultimodalModelWrapper):
             elif not greedy and self.rng == "torch_buffer":   # the same draws, pre-drawn by torch into a buffer
                 noise = self._draw_noise(steps, c.numel(), self.gpt_cfg["vocab_size"])
             self._step_seed += 1
-            out.append(self._gpt.sample(c, steps, temperature=gen_params["temperature"], top_k=gen_params["top_k"],
-                                        top_p=gen_params["top_p"], watermarker=wm, noise=noise, greedy=greedy,
-                                        seed=self._step_seed, torch_stream=stream))
+            eng, lane_stream = self._lane(ci % n_lanes)
+            kw = dict(temperature=gen_params["temperature"], top_k=gen_params["top_k"], top_p=gen_params["top_p"],
+                      watermarker=wm, noise=noise, greedy=greedy, seed=self._step_seed, torch_stream=stream)
+            if lane_stream is None:
+                out.append(eng.sample(c, steps, defer_check=n_lanes > 1, **kw))
+            else:
+                # NOT wait_stream(main): lane 0's generation was just enqueued there and the lanes must overlap it
+                if noise is not None:
+                    lane_stream.wait_stream(main)         # (legacy torch_buffer mode: the noise was drawn on `main`)
+                else:
+                    lane_stream.wait_event(ready)
+                with torch.cuda.stream(lane_stream):
+                    o = eng.sample(c, steps, defer_check=True, **kw)
+                o.record_stream(main)
+                out.append(o)
+        if n_lanes > 1:
+            for k in range(1, n_lanes):
+                main.wait_stream(self._lane_streams[k - 1])
+            _lib.check_device_flag()
         codes = out[0] if len(out) == 1 else torch.cat(out, dim=0)
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
         return codes
 
     def codes_to_images(self, codes):
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
-        images = self._vqgan.decode(codes)
+        mb = self.max_batch
+        images = self._vqgan.decode(codes) if codes.shape[0] <= mb else torch.cat(
+            [self._vqgan.decode(codes[i:i + mb]) for i in range(0, codes.shape[0], mb)], dim=0)
         assert self.is_images_shaped(images), f"Images shape: {images.shape}"
         return images
 
     def images_to_codes(self, images):
         assert self.is_images_shaped(images), f"Images shape: {images.shape}"
-        codes = self._vqgan.encode(images)
+        mb = self.max_batch
+        codes = self._vqgan.encode(images) if images.shape[0] <= mb else torch.cat(
+            [self._vqgan.encode(images[i:i + mb]) for i in range(0, images.shape[0], mb)], dim=0)
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
         return codes
