@@ -48,13 +48,14 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--no-anole", action="store_true", help="skip the Anole-7B extra block (one ~7 s step + warm-up)")
     ap.add_argument("--lanes", type=int, default=2, help="extra block: this many batches of 16 on concurrent engine lanes (1 = skip)")
     ap.add_argument("--vqgan-precision", choices=["3xtf32", "tf32", "bf16x3", "bf16x3-dec"], default="bf16x3")
     ap.add_argument("--rng", choices=["torch", "philox"], default="torch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--small", action="store_true", help="tiny shapes (plumbing check only; number is INVALID)")
-    ap.add_argument("--workload", default="all", choices=["all", "taming", "rar_xl", "detect"],
+    ap.add_argument("--workload", default="all", choices=["all", "taming", "rar_xl", "detect", "anole"],
                     help="all = Taming headline line + extra_workloads {rar_xl, detect_only}; rar_xl / detect = only "
                          "that block as the line")
     return ap.parse_args()
@@ -660,6 +661,84 @@ def run_detect(args, rank, world, dev, L, peaks):
     return blk
 
 
+ANOLE_METRIC = "watermarked 512x512 images/sec end-to-end (text prompt -> sample -> decode -> detect), Anole-7B shapes, 8 images/GPU"
+ANOLE_PROMPTS = ["a photo of a red bus parked next to a building on a sunny day", "two cats sleeping on a couch",
+                 "a plate of food with broccoli and rice on a wooden table", "a man riding a wave on a surfboard",
+                 "a kitchen with a stove a sink and a window", "a group of people flying kites in a park",
+                 "a close up of a pizza on a table", "a train traveling down tracks next to a forest"]
+
+
+def run_anole(args, rank, world, dev, L, peaks):
+    """BASELINE.json configs[3]: Anole-7B text -> image 512x512, watermark on (here: 8 images = 16 guided rows per GPU per
+    step at every N, random-init bf16 weights at the 7B shapes, synthetic prompts through the wrapper's stand-in tokenizer).
+    A step takes ~7 s, so this block times ONE step after ONE warm-up (stated in `steps` / `warmup`)."""
+    import torch
+    import torch.distributed as dist
+    from wmar_b200 import _lib
+    from wmar_b200.models.chameleon_wrapper import ChameleonARMMWrapper
+    from wmar_b200.watermarking import create_watermarker_from_string
+    B = 8
+    torch.manual_seed(0)
+    m = ChameleonARMMWrapper(max_batch=B, device=dev, vqgan_precision=args.vqgan_precision)
+    wm_string = "fixed-stratifiedrand-h=0-d=2.0-g=0.25"
+    wm = create_watermarker_from_string(m.get_vq(), m.get_total_vocab_size(), wm_string, dev)
+    m.set_watermarker(wm)
+    torch.manual_seed(1 + 1000 * rank)
+    cond = list(enumerate(ANOLE_PROMPTS))
+    gp = {"temperature": 0.9, "top_p": 0.9}
+    img_pin = torch.empty((B, 3, 512, 512), dtype=torch.float32).pin_memory()
+
+    def step():
+        codes = m.sample(cond, gp, apply_watermark=True)
+        e_s.record()
+        imgs = m.codes_to_images(codes)
+        e_d.record()
+        st = wm.detect_stats(codes)
+        img_pin.copy_(imgs, non_blocking=True)
+        return st
+
+    e0, e_s, e_d, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = L.wmar_launch_count()
+    e0.record()
+    st = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = L.wmar_launch_count() - launches0
+    tt = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(e_s), e_s.elapsed_time(e_d)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms, t_s, t_d = tt.tolist()
+    _lib.check(L.wmar_check_device_flag(_lib.current_stream()))
+    p_max = max(len(r) for r in m.prompt_rows(ANOLE_PROMPTS))
+    by = m._eng.algorithmic_bytes(B, p_max, 1024)
+    pk = float(peaks.get("hbm_gbs", 6650.0))
+    blk = {"metric": ANOLE_METRIC, "value": world * B / (t_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1,
+           "ms_per_step": t_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16 weights / activations as the reference (fp32 accumulate); VQGAN 3x3 convs: " + args.vqgan_precision,
+           "data": "synthetic",
+           "config": {"workload": "anole_7b_512_B8_cfg3.0_1.2_T0.9_p0.9_wm_fixed_h0_d2_g0.25", "batch_per_gpu": B,
+                      "global_batch": B * world, "tokens_per_image": 1024, "watermark": wm_string, "gen_params": gp,
+                      "parallelism": f"replicas x{world}", "l2": "inputs larger than L2 (13.5 GB of bf16 weights streamed per pass)"},
+           "e2e": {"value": world * B / (t_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * p_max * 3 * B,
+                   "d2h_bytes_per_step": img_pin.numel() * 4, "ms_per_step": t_ms,
+                   "note": "the timed step IS the end-to-end call: host prompts in, images copied to pinned host memory"},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "kernel": "Anole-7B decode loop (prompt + 1023 passes over 16 rows, bf16 skinny GEMMs + GQA attention + CFG / watermark / sampler)",
+                        "achieved": by / t_s / 1e6, "peak": pk, "peak_source": "measured" if peaks else "fallback", "unit": "GB/s",
+                        "frac": by / t_s / 1e6 / pk, "traffic": None, "algorithmic_bytes_per_launch": by, "ms_per_launch": t_s,
+                        "phase_ms_per_step": {"sample": t_s, "vqgan_decode_512": t_d, "detect+rest": t_ms - t_s - t_d}},
+           "detector": {"n_green_mean": float(st["n_green"].float().mean()), "z_mean": float(st["z"].mean())}}
+    del m, wm
+    torch.cuda.empty_cache()
+    return blk
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -673,13 +752,15 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()  # raises if the CUDA library is missing
     peaks = load_peaks()
-    runners = {"taming": run_taming, "rar_xl": run_rar_xl, "detect": run_detect}
+    runners = {"taming": run_taming, "rar_xl": run_rar_xl, "detect": run_detect, "anole": run_anole}
     if args.workload == "all":
         line = run_taming(args, rank, world, dev, L, peaks)
         extra = {}
         if "_lanes_block" in line:
             extra["taming_concurrent_lanes"] = line.pop("_lanes_block")
-        for name, key in (("rar_xl", "rar_xl"), ("detect", "detect_only")):
+        for name, key in (("rar_xl", "rar_xl"), ("detect", "detect_only"), ("anole", "anole_7b")):
+            if name == "anole" and (args.no_anole or args.small):
+                continue
             try:
                 extra[key] = runners[name](args, rank, world, dev, L, peaks)
             except Exception as e:  # an extra block must never take the headline line down
