@@ -202,6 +202,31 @@ def test_chameleon_wrapper_roundtrip_small():
     assert float(p_wm.max()) < 1e-6 < float(p_0.min())                          # delta 4: the watermark is unmistakable
 
 
+def test_chameleon_wrapper_lanes_equal_sequential_chunk_loop():
+    """ChameleonARMMWrapper.sample with more prompts than max_batch: chunks on concurrent engine lanes (shared weights, own
+    KV cache / stream) == the sequential chunk loop, bit for bit, sampled and greedy, including the first call (lanes are
+    created before any work is enqueued)."""
+    from wmar_b200.models.chameleon_wrapper import ChameleonARMMWrapper
+    from wmar_b200.watermarking import create_watermarker_from_string
+    cfg = dict(vocab_size=16384, dim=256, n_layers=2, n_heads=2, n_kv_heads=2, ffn_hidden=384, norm_eps=1e-5, rope_theta=10000.0,
+               qk_normalization=True)
+    vq = dict(ch=128, out_ch=3, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(), in_channels=3, resolution=32,
+              z_channels=256, n_embed=8192, embed_dim=256)
+    cond = [(i, p) for i, p in enumerate(["a red bus", "two cats on a couch", "a dog", "a kitchen with a stove", "pizza"])]
+    res = {}
+    for lanes in (1, 2):
+        m = ChameleonARMMWrapper(model_cfg=cfg, vq_cfg=vq, max_batch=2, image_tokens_per_image=256, lanes=lanes,
+                                 tokenize=lambda p: [16384 - 1 - (len(w) % 7) for w in p.split()])
+        wm = create_watermarker_from_string(m.get_vq(), m.get_total_vocab_size(), "fixed-stratifiedrand-h=0-d=4.0-g=0.25", m.device)
+        m.set_watermarker(wm)
+        torch.manual_seed(3)
+        a = m.sample(cond, {"temperature": 0.9, "top_p": 0.9}, apply_watermark=True)       # 3 chunks: 2 + 2 + 1 prompts
+        g = m.sample(cond, {"temperature": 0.9, "top_p": 0.9}, apply_watermark=True, greedy=True)
+        res[lanes] = (a.cpu(), g.cpu(), torch.rand(4, device="cuda").cpu())
+    for x, y in zip(res[1], res[2]):
+        assert torch.equal(x, y)
+
+
 def test_two_group_mode_is_bit_identical_to_three_groups():
     """Text-only prompts: image-conditioned rows == unconditioned rows; computing them once (n_groups = 2) must give the
     same ids and the same mixed logits as the reference's three row groups."""

@@ -48,6 +48,18 @@ class ChameleonEngine:
         self._tensors = tensors
         self._create()
 
+    def clone_lane(self):
+        """A second engine over the SAME weight tensors with its own KV cache / scratch / graphs: an independent lane whose
+        generations run concurrently with this one's on another CUDA stream (gpt_engine.TamingGPTEngine.clone_lane)."""
+        lane = object.__new__(type(self))
+        for k in ("device", "n_layer", "n_head", "n_kv_head", "image_tokens", "max_seq", "max_batch", "norm_eps", "rope_theta",
+                  "qk_norm", "vocab_size", "dim", "ffn_hidden"):
+            setattr(lane, k, getattr(self, k))
+        lane.handle = None
+        lane._tensors = self._tensors
+        lane._create()
+        return lane
+
     def _create(self):
         L = _lib.lib()
         if self.handle is not None:
@@ -72,7 +84,7 @@ class ChameleonEngine:
 
     @torch.no_grad()
     def sample(self, prompts3, steps=1024, guidance_text=3.0, guidance_image=1.2, temperature=1.0, top_p=None,
-               watermarker=None, noise=None, greedy=False, seed=0, return_logits=False, torch_stream=None):
+               watermarker=None, noise=None, greedy=False, seed=0, return_logits=False, torch_stream=None, defer_check=False):
         """prompts3: 3B token-id lists (B full-conditioned, B image-conditioned, B unconditioned rows, each ending in
         <boi>; chameleon.py:351-372).  Returns ids int64[B, steps] (+ the mixed logits of the image-token window)."""
         R = len(prompts3)
@@ -108,7 +120,8 @@ class ChameleonEngine:
                                                    _lib.ptr(pr), _lib.ptr(plen), p_max, p_max, B, n_groups, float(guidance_text),
                                                    float(guidance_image), steps, _lib.ptr(noise), _lib.ptr(out),
                                                    _lib.ptr(logits), _lib.current_stream()))
-            _lib.check_device_flag()   # raises on an out-of-range context sum / top-p overflow (device-side checks)
+            if not defer_check:        # (lanes: the caller checks once after joining the streams)
+                _lib.check_device_flag()   # raises on an out-of-range context sum / top-p overflow (device-side checks)
         self._keepalive = (pr, plen, noise)
         self.last_n_groups = n_groups
         return (out, logits) if return_logits else out

@@ -41,7 +41,7 @@ def _stand_in_tokenizer(prompt):
 
 class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
     def __init__(self, modelpath=None, *, state_dict=None, tokenizer_state_dict=None, model_cfg=None, vq_cfg=None,
-                 tokenize=None, bpe2img=None, device="cuda", max_batch=8, vqgan_precision="bf16x3", seed=0, rng="torch",
+                 tokenize=None, bpe2img=None, device="cuda", max_batch=8, vqgan_precision="bf16x3", seed=0, rng="torch", lanes=2,
                  guidance_text=3.0, guidance_image=1.2, image_tokens_per_image=1024, alive_ids_path=None):
         super().__init__()
         self._device = torch.device(device)
@@ -82,6 +82,8 @@ class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
         self.dim_z = self.vq_cfg["z_channels"]
         self._eng = None
         self._vqgan = None
+        self.lanes = max(1, int(lanes))
+        self._lane_engines, self._lane_streams = [], []
         self._step_seed = seed
         self.sync_weights()
 
@@ -104,6 +106,7 @@ class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
                                         qk_norm=c.get("qk_normalization", True), device=self._device)
         else:
             self._eng.sync_weights(self._state)
+        self._lane_engines, self._lane_streams = [], []   # lanes borrow the engine's tensors: rebuilt on demand
         v = self.vq_cfg
         ecfg = dict(family=0, ch=v["ch"], ch_mult=tuple(v["ch_mult"]), num_res_blocks=v["num_res_blocks"],
                     attn_resolution=0, resolution=v["resolution"], z_channels=v["z_channels"], embed_dim=v["embed_dim"],
@@ -125,6 +128,15 @@ class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
         unc = [[BOS_ID, BEGIN_IMAGE] for _ in full]
         return full + img + unc
 
+    def _lane(self, k):
+        """Engine + stream of lane k (lane 0 = the wrapper's own engine on the caller's stream); see TamingARMMWrapper."""
+        if k == 0:
+            return self._eng, None
+        while len(self._lane_engines) < k:
+            self._lane_engines.append(self._eng.clone_lane())
+            self._lane_streams.append(torch.cuda.Stream(device=self.device))
+        return self._lane_engines[k - 1], self._lane_streams[k - 1]
+
     # conditioning: list of size [b] of (index, prompt) coco tuples.  Returns detached BPE codes [b, 1024]
     def sample(self, conditioning, gen_params=None, apply_watermark=False, greedy=False):
         gen_params = gen_params or {}
@@ -134,7 +146,15 @@ class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
         V = self.cfg["vocab_size"]
         out = []
         mb = self._eng.max_batch
-        for i in range(0, len(prompts), mb):
+        n_chunks = (len(prompts) + mb - 1) // mb
+        n_lanes = min(self.lanes, n_chunks)      # chunk i -> lane i % n_lanes, concurrently (weights shared)
+        if n_lanes - 1 > len(self._lane_engines):
+            self._lane(n_lanes - 1)              # before any work of this call is enqueued (see TamingARMMWrapper.sample)
+            torch.cuda.synchronize(self.device)
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for ci, i in enumerate(range(0, len(prompts), mb)):
             rows = self.prompt_rows(prompts[i:i + mb])
             b = len(rows) // 3
             noise, stream = None, None
@@ -143,10 +163,24 @@ class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
             elif not greedy and self.rng == "torch_buffer":
                 noise = self._draw_noise(steps, b, V)
             self._step_seed += 1
-            out.append(self._eng.sample(rows, steps, self.guidance_text, self.guidance_image,
-                                        temperature=gen_params.get("temperature", 1.0), top_p=gen_params.get("top_p"),
-                                        watermarker=wm, noise=noise, greedy=greedy, seed=self._step_seed,
-                                        torch_stream=stream))
+            eng, lane_stream = self._lane(ci % n_lanes)
+            kw = dict(temperature=gen_params.get("temperature", 1.0), top_p=gen_params.get("top_p"), watermarker=wm,
+                      noise=noise, greedy=greedy, seed=self._step_seed, torch_stream=stream)
+            if lane_stream is None:
+                out.append(eng.sample(rows, steps, self.guidance_text, self.guidance_image, defer_check=n_lanes > 1, **kw))
+            else:
+                if noise is not None:
+                    lane_stream.wait_stream(main)
+                else:
+                    lane_stream.wait_event(ready)
+                with torch.cuda.stream(lane_stream):
+                    o = eng.sample(rows, steps, self.guidance_text, self.guidance_image, defer_check=True, **kw)
+                o.record_stream(main)
+                out.append(o)
+        if n_lanes > 1:
+            for k in range(1, n_lanes):
+                main.wait_stream(self._lane_streams[k - 1])
+            _lib.check_device_flag()
         codes = out[0] if len(out) == 1 else torch.cat(out, dim=0)
         assert self.is_codes_shaped(codes), f"Codes shape: {codes.shape}"
         return codes
