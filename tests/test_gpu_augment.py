@@ -131,3 +131,29 @@ def test_evaluation_log_values_match_the_reference():
                 else:
                     assert abs(got_psnr[b] - want_psnr[b]) <= 0.05, (transform, j, b, got_psnr[b], want_psnr[b])
     assert n_checked >= 12
+
+
+def test_detect_host_batches_equals_plain_loop():
+    """Bulk detection over pinned host batches (copy stream + two staging buffers) == the plain per-batch loop."""
+    from oracle import gpt as ogpt
+    from oracle import vqgan as ov
+    from wmar_b200.evaluate import detect_host_batches
+    from wmar_b200.models import TamingARMMWrapper
+    from wmar_b200.watermarking import create_watermarker_from_string
+    V = 16384
+    gpt_cfg = dict(vocab_size=V, block_size=64, n_layer=1, n_head=4, n_embd=256)
+    dd = dict(ov.TAMING_CFG, ch=128, ch_mult=(1, 2), resolution=32, attn_resolutions=(16,))
+    state = {"transformer." + k: v for k, v in ogpt.synthetic_gpt_weights(V, 64, 1, 4, 256, seed=7).items()}
+    state.update({"first_stage_model." + k: v for k, v in ov.synthetic_taming_vqgan_weights(dd, seed=8).items()})
+    m = TamingARMMWrapper(state_dict=state, gpt_cfg=gpt_cfg, dd_cfg=dd, device="cuda", max_batch=4)
+    wm = create_watermarker_from_string(m.get_vq(), V, "linear-stratifiedrand-h=1-d=2.0-g=0.25", "cuda")
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.rand(4, 3, 32, 32, generator=g) * 2 - 1).pin_memory() for _ in range(5)]
+    batches.append((torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).pin_memory())        # ragged tail
+    got = detect_host_batches(m, wm, batches)
+    assert got.shape == (6, 4, 4)
+    for i, hb in enumerate(batches):
+        st = wm.detect_stats(m.images_to_codes(hb.cuda()))
+        for j, k in enumerate(("n_green", "n_scored", "z", "pvalue")):
+            assert torch.equal(got[i, : hb.shape[0], j], st[k].double().cpu()), (i, k)
+    assert detect_host_batches(m, wm, []).shape[0] == 0

@@ -73,3 +73,57 @@ def compute_metrics(batch_log, key, watermarker, metric_names=("pvalue", "l0", "
                     raise ValueError(f"Metric {name} not found")
             out[transform].append((param, m))
     return out
+
+
+class _HostDetectState:
+    """Copy stream, two device staging buffers and the pinned result buffer of detect_host_batches, kept on the model
+    between calls (page-locking a fresh result buffer and creating a stream per call cost up to tens of ms)."""
+
+    def __init__(self, dev, shape, n_batches, n_keys):
+        self.shape, self.n_batches, self.n_keys = tuple(shape), n_batches, n_keys
+        self.copy = torch.cuda.Stream(device=dev)
+        self.stage = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.out = torch.empty((n_batches, shape[0], n_keys), dtype=torch.float64).pin_memory()
+
+
+@torch.no_grad()
+def detect_host_batches(model, watermarker, host_batches, keys=("n_green", "n_scored", "z", "pvalue")):
+    """Detection-only job (BASELINE configs[4]) over images that live in (pinned) HOST memory: for every batch
+    images_to_codes -> watermarker.detect_stats, with the host->device copy of batch i + 1 running on a copy stream while
+    batch i is encoded (two device staging buffers).  Returns a float64 pinned host tensor [n_batches, B, len(keys)]
+    (filled asynchronously, synchronised before returning; the buffer is reused by the next call with the same shapes)."""
+    host_batches = list(host_batches)
+    if not host_batches:
+        return torch.empty((0, 0, len(keys)), dtype=torch.float64)
+    dev = model.device
+    main = torch.cuda.current_stream(dev)
+    shape = host_batches[0].shape
+    stt = getattr(model, "_host_detect_state", None)
+    if stt is None or stt.shape != tuple(shape) or stt.n_batches < len(host_batches) or stt.n_keys != len(keys):
+        stt = model._host_detect_state = _HostDetectState(dev, shape, len(host_batches), len(keys))
+    copy, stage, out = stt.copy, stt.stage, stt.out[: len(host_batches)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [None, None]
+    copy.wait_stream(main)
+
+    def upload(i):
+        k = i % 2
+        with torch.cuda.stream(copy):
+            if free[k] is not None:
+                copy.wait_event(free[k])                # batch i - 2 has been consumed
+            stage[k][: host_batches[i].shape[0]].copy_(host_batches[i], non_blocking=True)
+            ready[k].record(copy)
+
+    upload(0)
+    for i, hb in enumerate(host_batches):
+        if i + 1 < len(host_batches):
+            upload(i + 1)
+        k = i % 2
+        main.wait_event(ready[k])
+        st = watermarker.detect_stats(model.images_to_codes(stage[k][: hb.shape[0]]))
+        free[k] = torch.cuda.Event()
+        free[k].record(main)
+        res = torch.stack([st[key].to(torch.float64) for key in keys], dim=1)      # [B, n_keys] on the device: ONE copy
+        out[i, : hb.shape[0]].copy_(res, non_blocking=True)
+    main.synchronize()
+    return out
