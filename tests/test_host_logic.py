@@ -289,3 +289,19 @@ def test_precompute_imagenet_codes_host_logic(tmp_path):
     assert sorted(os.listdir(out / "codes")) == [f"{c}:{k:04}.npy" for c in (0, 999) for k in range(3)]
     assert sorted(os.listdir(out / "images")) == [f"{c}:{k:04}.png" for c in (0, 999) for k in range(3)]
     assert np.load(out / "codes" / "0:0000.npy").shape == (16,)
+
+
+def test_group_batches_preserves_order_and_content():
+    """generate --lanes: consecutive planned batches are grouped for one wrapper call; flattening the groups gives back the
+    planned batches in order (so the wrapper's chunking by max_batch == batch_size reproduces them)."""
+    from wmar_b200.generate import expand_conditionings, group_batches, plan_batches
+    inputs = expand_conditionings(",".join(str(i) for i in range(23)), 2)
+    for bs, chunks in ((16, 1), (5, 2), (7, 3)):
+        for chunk_id in range(chunks):
+            planned = list(plan_batches(inputs, bs, chunk_id, chunks))
+            for lanes in (1, 2, 3):
+                groups = list(group_batches(iter(planned), lanes))
+                assert [b for g in groups for b in g] == planned
+                assert all(len(g) == lanes for g in groups[:-1]) and 1 <= len(groups[-1]) <= lanes if groups else True
+                flat = [c for g in groups for _, batch, _ in g for c in batch]
+                assert flat == [c for _, batch, _ in planned for c in batch]

@@ -21,6 +21,18 @@ import sys
 import numpy as np
 
 
+def group_batches(batches, lanes):
+    """Consecutive runs of `lanes` planned batches (the last group may be shorter); lanes = 1 -> one batch per group."""
+    group = []
+    for item in batches:
+        group.append(item)
+        if len(group) == lanes:
+            yield group
+            group = []
+    if group:
+        yield group
+
+
 def plan_batches(all_inputs, batch_size, chunk_id=0, num_chunks=1):
     """generate.py:179-207 -- split into batches (last may be smaller), keep the 1-based running count per
     conditioning even for batches another chunk owns, return this chunk's [(batch_idx, batch, cond_indices)]."""
@@ -135,6 +147,8 @@ def get_parser():
     p.add_argument("--num_samples_per_conditioning", type=int, default=1)
     p.add_argument("--conditioning", type=str)
     p.add_argument("--batch_size", type=int, nargs="?", default=10)
+    p.add_argument("--lanes", type=int, default=2,
+                   help="consecutive batches sampled concurrently on engine lanes of one GPU (1 = the reference's sequential loop)")
     p.add_argument("--top_k", type=int, nargs="?", default=600)
     p.add_argument("--temperature", type=float, nargs="?", default=1.0)
     p.add_argument("--top_p", type=float, nargs="?", default=0.92)
@@ -212,12 +226,22 @@ def main(argv=None):
         eval_params = {"metric_names": ["pvalue", "l0", "psnr", "bpp"], "augmentations": default_augmentations(),
                        "max_roundtrips": 1, "orig_only": False}
     n_done = 0
-    for batch_idx, batch, cond_indices in plan_batches(all_inputs, args.batch_size, chunk_id, num_chunks):
-        codes = model.sample(batch, gen_params, apply_watermark=watermarker is not None)
-        batch_log = {"batch": batch}
-        fill_batch_log(batch_log, str(watermarker), model, codes, eval_params)
-        save_batch_log(batch_log, args.outdir, watermarker, eval_params, cond_indices)
-        n_done += len(batch)
+    # `--lanes` consecutive batches are sampled by ONE wrapper call: the wrapper cuts the concatenated conditioning back into
+    # the same batches (max_batch == batch_size) and runs them on concurrent engine lanes -- same codes as one call per batch
+    # (only when a batch is ONE engine call -- otherwise the concatenation would be cut differently than the batches)
+    cap = {"taming": 16, "rar": 8}.get(args.model, 5)
+    lanes = max(1, args.lanes) if args.batch_size <= cap else 1
+    for group in group_batches(plan_batches(all_inputs, args.batch_size, chunk_id, num_chunks), lanes):
+        conds = [c for _, batch, _ in group for c in batch]
+        codes_all = model.sample(conds, gen_params, apply_watermark=watermarker is not None)
+        o = 0
+        for batch_idx, batch, cond_indices in group:
+            codes = codes_all[o:o + len(batch)]
+            o += len(batch)
+            batch_log = {"batch": batch}
+            fill_batch_log(batch_log, str(watermarker), model, codes, eval_params)
+            save_batch_log(batch_log, args.outdir, watermarker, eval_params, cond_indices)
+            n_done += len(batch)
     print(f"[chunk {chunk_id}/{num_chunks}] wrote {n_done} images to {args.outdir}")
     return 0
 
