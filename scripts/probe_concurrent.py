@@ -35,6 +35,7 @@ def enqueue(i, seed):
                                      _lib.ptr(outs[i]), None, _lib.current_stream()))
 
 
+torch.cuda.synchronize()
 for i in range(N):
     enqueue(i, 1 + i)
 torch.cuda.synchronize()

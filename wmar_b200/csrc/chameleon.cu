@@ -526,6 +526,9 @@ int wmar_cham_create(const wmar_cham_config *cfg, const void *const *d_weights, 
     WMAR_CUDA_CHECK(cudaMemset(g->rowpos, 0xff, sizeof(int) * 16));
     g->graph = nullptr; g->exec = nullptr; g->graph_smem = 0; g->graph_B = 0;
     g->launches_per_pass = 5 * cfg->n_layer + 5;
+    // the zero-fills above went to the legacy default stream: finish them before the handle can be used from a
+    // non-blocking stream (a second engine lane otherwise saw them land in the middle of its first generation)
+    WMAR_CUDA_CHECK(cudaDeviceSynchronize());
     *out = g;
     return WMAR_OK;
 }

@@ -812,6 +812,9 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
             g->launches_per_step = 4 * cfg->n_layer + 4;
         }
     }
+    // the zero-fills above went to the legacy default stream: finish them before the handle can be used from a
+    // non-blocking stream (a second engine lane otherwise saw them land in the middle of its first generation)
+    WMAR_CUDA_CHECK(cudaDeviceSynchronize());
     *out = g;
     return WMAR_OK;
 }

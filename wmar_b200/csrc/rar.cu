@@ -763,6 +763,9 @@ int wmar_rar_create(const wmar_rar_config *cfg, const void *const *d_weights, in
             WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
     }
+    // the zero-fills above went to the legacy default stream: finish them before the handle can be used from a
+    // non-blocking stream (a second engine lane otherwise saw them land in the middle of its first generation)
+    WMAR_CUDA_CHECK(cudaDeviceSynchronize());
     *out = g;
     return WMAR_OK;
 }
