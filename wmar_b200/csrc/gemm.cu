@@ -77,7 +77,7 @@ int launch_skinny_gemm(int pro, int epi, const GemmArgs &a, cudaStream_t stream)
     WMAR_REQUIRE(a.ldx % 4 == 0 && a.ldy % 4 == 0, "row strides must be multiples of 4 floats");
     if (gemm_engine() == 0 && tc_gemm_eligible(a)) return launch_tc_gemm(pro, epi, a, stream);
     WMAR_REQUIRE(a.N % GEMM_NT == 0, "N must be a multiple of 64");
-    WMAR_REQUIRE(a.splits >= 1 && a.K % (a.splits * GEMM_KI) == 0, "K must be a multiple of splits*16");
+    WMAR_REQUIRE(a.splits >= 1 && a.K % GEMM_KI == 0 && a.K / GEMM_KI >= a.splits, "K must be a multiple of 16 with at least one 16-float chunk per split");
     WMAR_REQUIRE(a.splits == 1 || (a.ws != nullptr && a.counters != nullptr), "split-K needs a workspace");
 #define WMAR_CASE(P, E) \
     if (pro == P && epi == E) return launch_t<P, E>(a, stream);
@@ -95,17 +95,20 @@ int launch_skinny_gemm(int pro, int epi, const GemmArgs &a, cudaStream_t stream)
 
 int pick_splits(int N, int K, int n_sms) {
     const int tiles = N / GEMM_NT;
-    // about one full wave at two CTAs per SM; WMAR_GEMM_WAVE=1: one CTA per SM, so that the NEXT kernel's CTAs fit
-    // beside this kernel's (2 x 96 KB of shared memory, 2 x 32 K registers) and stream their first weights early
+    // ONE wave: tiles x splits must not exceed the resident CTA slots (two 96 KB CTAs per SM).  A grid that spills into a
+    // second wave costs a latency-bound kernel a whole extra main loop, and the spilled CTAs are the LAST split's, i.e. the
+    // reducers everybody waits for (RAR-XL shapes in round 2: qkv (60,5) = 300, fc1 (80,4) = 320, fc2 (20,16) = 320 CTAs on
+    // 296 slots ran at 17.7 / 20.5 / 19.2 us per launch against 10.2 us for proj (20,10)).  Splits need not divide K: the
+    // kernel cuts the 16-float chunks into near-equal parts.  Every split keeps >= 8 chunks (one per warp).
+    // WMAR_GEMM_WAVE=1: one CTA per SM, so that the NEXT kernel's CTAs (or another lane's) fit beside this kernel's.
     static const int wave = []() { const char *e = getenv("WMAR_GEMM_WAVE"); return e ? atoi(e) : 2; }();
-    const int target = wave == 1 ? n_sms - 8 : 2 * n_sms - 16;
-    int best = 1;
-    for (int s = 1; s <= 64; s++) {
-        if (K % (s * GEMM_KI) != 0 || K / (s * GEMM_KI) < GEMM_WARPS) continue;
-        best = s;
-        if (tiles * s >= target) break;
-    }
-    return best;
+    const int slots = wave == 1 ? n_sms : 2 * n_sms;
+    int s = slots / (tiles > 0 ? tiles : 1);
+    const int by_chunks = (K / GEMM_KI) / GEMM_WARPS;
+    if (s > by_chunks) s = by_chunks;
+    if (s > 64) s = 64;
+    if (s < 1) s = 1;
+    return s;
 }
 
 size_t gemm_ws_floats(int N, int K, int splits_v0, int n_sms) {

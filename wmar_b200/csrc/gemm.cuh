@@ -176,10 +176,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) skinny_gemm_kernel(GemmArgs a
     const int tile = blockIdx.x, split = blockIdx.y;
     const int n0 = tile * GEMM_NT;
     // K is cut into 16-float chunks; chunk c of this split goes to warp c % 8, so the 8 warps of a CTA sweep each
-    // weight row in 512-byte contiguous strides (any K that is a multiple of 16 * splits works)
-    const int KS = a.K / a.splits;
-    const int chunks = KS / GEMM_KI;
-    const int kw0 = split * KS + warp * GEMM_KI;
+    // weight row in 512-byte contiguous strides (any K that is a multiple of 16 works)
+    // split s owns chunks [total * s / splits, total * (s + 1) / splits): equal parts when splits divides the chunk count
+    // (every Taming shape), otherwise parts that differ by one chunk -- which lets pick_splits() fit ANY shape into one wave
+    const int total_chunks = a.K / GEMM_KI;
+    const int c0 = (int)((long long)total_chunks * split / a.splits);
+    const int chunks = (int)((long long)total_chunks * (split + 1) / a.splits) - c0;
+    const int kw0 = c0 * GEMM_KI + warp * GEMM_KI;
     const int iters = warp < chunks ? (chunks - warp + GEMM_WARPS - 1) / GEMM_WARPS : 0;
     constexpr int KSTEP = GEMM_WARPS * GEMM_KI;
 
