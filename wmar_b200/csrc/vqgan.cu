@@ -15,6 +15,8 @@
 //   AttnBlock = norm.g, norm.b, q.w, q.b, k.w, k.b, v.w, v.b, proj_out.w, proj_out.b
 #include <vector>
 
+#include <functional>
+
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
 #include "vqgan_kernels.cuh"
@@ -66,7 +68,14 @@ struct wmar_vqgan {
     double2 *gn_partial;
     double flops_enc, flops_dec;
     int enc_out_buf, latent;  // buffer holding the encoder output (pre-quant z), latent side
-    const float *enc_images = nullptr;   // the caller's NCHW images of the running encode call (conv_in3_kernel reads them)
+    const float *enc_images = nullptr;   // NCHW images of the running encode call (conv_in3_kernel reads them)
+    // CUDA graphs of the two directions (round 2): ~150 / ~110 host launches + tensor-map encodes per call became ONE
+    // launch -- a descheduled host thread showed up as 56 ms decodes among 20.3 ms ones.  Graphs need fixed addresses: the
+    // caller's codes / images are copied into (out of) engine-owned staging buffers around the graph launch.
+    bool use_graph = true;
+    int64_t *g_codes = nullptr;          // [max_batch][latent^2]
+    float *g_images = nullptr;           // [max_batch][3][R][R]
+    std::vector<cudaGraphExec_t> dec_exec, enc_exec;   // one per batch size, captured on first use
 };
 
 namespace {
@@ -511,6 +520,16 @@ int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(attn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_out3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CO_SMEM_BYTES));
+    WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SM_ALLOC));
+    WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SM_ALLOC));
+    {
+        const char *e = getenv("WMAR_VQ_GRAPH");
+        v->use_graph = !(e && e[0] == '0');
+        v->dec_exec.assign((size_t)cfg->max_batch + 1, nullptr);
+        v->enc_exec.assign((size_t)cfg->max_batch + 1, nullptr);
+        WMAR_CUDA_CHECK(cudaMalloc(&v->g_codes, sizeof(int64_t) * tokens));
+        WMAR_CUDA_CHECK(cudaMalloc(&v->g_images, sizeof(float) * (size_t)cfg->max_batch * 3 * R * R));
+    }
     WMAR_CUDA_CHECK(cudaDeviceSynchronize());
     *out = v;
     return WMAR_OK;
@@ -523,10 +542,13 @@ void wmar_vqgan_destroy(wmar_vqgan *v) {
         for (Op &o : *ops) { cudaFree(o.wlo); cudaFree(o.wb1); cudaFree(o.wb2); }
     for (int i = 0; i < 6; i++) cudaFree(v->buf[i]);
     cudaFree(v->dots); cudaFree(v->zz); cudaFree(v->ee); cudaFree(v->gn_partial);
+    for (cudaGraphExec_t e : v->dec_exec) if (e) cudaGraphExecDestroy(e);
+    for (cudaGraphExec_t e : v->enc_exec) if (e) cudaGraphExecDestroy(e);
+    cudaFree(v->g_codes); cudaFree(v->g_images);
     delete v;
 }
 
-int wmar_vqgan_decode(wmar_vqgan *v, const int64_t *d_codes, int64_t B, float *d_images, void *stream) {
+static int vqgan_decode_eager(wmar_vqgan *v, const int64_t *d_codes, int64_t B, float *d_images, void *stream) {
     WMAR_REQUIRE(v && d_codes && d_images, "NULL argument");
     WMAR_REQUIRE(B >= 1 && B <= v->cfg.max_batch, "batch exceeds max_batch");
     cudaStream_t s = as_stream(stream);
@@ -538,7 +560,7 @@ int wmar_vqgan_decode(wmar_vqgan *v, const int64_t *d_codes, int64_t B, float *d
     return run_ops(v, v->dec, (int)B, d_images, s);
 }
 
-int wmar_vqgan_encode(wmar_vqgan *v, const float *d_images, int64_t B, int64_t *d_codes, void *stream) {
+static int vqgan_encode_eager(wmar_vqgan *v, const float *d_images, int64_t B, int64_t *d_codes, void *stream) {
     WMAR_REQUIRE(v && d_codes && d_images, "NULL argument");
     WMAR_REQUIRE(B >= 1 && B <= v->cfg.max_batch, "batch exceeds max_batch");
     cudaStream_t s = as_stream(stream);
@@ -568,6 +590,56 @@ int wmar_vqgan_encode(wmar_vqgan *v, const float *d_images, int64_t B, int64_t *
     WMAR_LAUNCH_CHECK();
     vq_argmin_kernel<<<tokens, 256, 0, s>>>(v->dots, v->zz, v->ee, d_codes, NE);
     WMAR_LAUNCH_CHECK();
+    return WMAR_OK;
+}
+
+// one direction as a cached CUDA graph over the engine's staging buffers (re-captured when the batch size changes)
+static int vqgan_capture(cudaGraphExec_t *exec, const std::function<int(cudaStream_t)> &body) {
+    if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
+    cudaStream_t cs;
+    WMAR_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    WMAR_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(cs);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+    cudaStreamDestroy(cs);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return set_error(WMAR_ERR_CUDA, "cudaStreamEndCapture (vqgan): %s%s", cudaGetErrorString(e));
+    const cudaError_t ei = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return set_error(WMAR_ERR_CUDA, "cudaGraphInstantiate (vqgan): %s%s", cudaGetErrorString(ei));
+    return WMAR_OK;
+}
+
+int wmar_vqgan_decode(wmar_vqgan *v, const int64_t *d_codes, int64_t B, float *d_images, void *stream) {
+    WMAR_REQUIRE(v && d_codes && d_images, "NULL argument");
+    WMAR_REQUIRE(B >= 1 && B <= v->cfg.max_batch, "batch exceeds max_batch");
+    if (!v->use_graph) return vqgan_decode_eager(v, d_codes, B, d_images, stream);
+    cudaStream_t s = as_stream(stream);
+    const size_t n_tok = (size_t)B * v->latent * v->latent, n_img = (size_t)B * 3 * v->cfg.resolution * v->cfg.resolution;
+    if (v->dec_exec[B] == nullptr) {
+        int rc = vqgan_capture(&v->dec_exec[B], [&](cudaStream_t cs) { return vqgan_decode_eager(v, v->g_codes, B, v->g_images, cs); });
+        if (rc) return rc;
+    }
+    WMAR_CUDA_CHECK(cudaMemcpyAsync(v->g_codes, d_codes, sizeof(int64_t) * n_tok, cudaMemcpyDeviceToDevice, s));
+    WMAR_CUDA_CHECK(cudaGraphLaunch(v->dec_exec[B], s));
+    WMAR_CUDA_CHECK(cudaMemcpyAsync(d_images, v->g_images, sizeof(float) * n_img, cudaMemcpyDeviceToDevice, s));
+    return WMAR_OK;
+}
+
+int wmar_vqgan_encode(wmar_vqgan *v, const float *d_images, int64_t B, int64_t *d_codes, void *stream) {
+    WMAR_REQUIRE(v && d_codes && d_images, "NULL argument");
+    WMAR_REQUIRE(B >= 1 && B <= v->cfg.max_batch, "batch exceeds max_batch");
+    if (!v->use_graph) return vqgan_encode_eager(v, d_images, B, d_codes, stream);
+    cudaStream_t s = as_stream(stream);
+    const size_t n_tok = (size_t)B * v->latent * v->latent, n_img = (size_t)B * 3 * v->cfg.resolution * v->cfg.resolution;
+    if (v->enc_exec[B] == nullptr) {
+        int rc = vqgan_capture(&v->enc_exec[B], [&](cudaStream_t cs) { return vqgan_encode_eager(v, v->g_images, B, v->g_codes, cs); });
+        if (rc) return rc;
+    }
+    WMAR_CUDA_CHECK(cudaMemcpyAsync(v->g_images, d_images, sizeof(float) * n_img, cudaMemcpyDeviceToDevice, s));
+    WMAR_CUDA_CHECK(cudaGraphLaunch(v->enc_exec[B], s));
+    WMAR_CUDA_CHECK(cudaMemcpyAsync(d_codes, v->g_codes, sizeof(int64_t) * n_tok, cudaMemcpyDeviceToDevice, s));
     return WMAR_OK;
 }
 
