@@ -226,14 +226,29 @@ __global__ void __launch_bounds__(CH_ATT_THREADS) cham_attn_kernel(const float *
         return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
     };
     constexpr int BATCH = 8;
+    auto cvt4 = [&](const uint2 u) {
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&u.x), b = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
+        return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+    };
+    // software pipeline: the 8 key rows of the NEXT round are requested before this round's dot products and shuffle
+    // reductions (at 1000 keys the kernel is a 260 MB stream per layer; load -> wait -> reduce -> load ran it at ~2 TB/s)
+    uint2 kraw[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) {
+        const int j = warp + 8 * u;
+        kraw[u] = j < p ? *reinterpret_cast<const uint2 *>(K + (size_t)j * HD + 4 * lane) : make_uint2(0u, 0u);
+    }
     for (int j0 = warp; j0 < nk; j0 += 8 * BATCH) {
         float4 k4[BATCH];
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             const int j = j0 + 8 * u;
-            if (j < p) k4[u] = ld4(K + (size_t)j * HD + 4 * lane);
-            else if (j == p) k4[u] = *reinterpret_cast<const float4 *>(sk + 4 * lane);   // this pass's own key
-            else k4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            k4[u] = j == p ? *reinterpret_cast<const float4 *>(sk + 4 * lane) : cvt4(kraw[u]);   // j == p: this pass's own key
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + 8 * BATCH + 8 * u;
+            kraw[u] = j < p ? *reinterpret_cast<const uint2 *>(K + (size_t)j * HD + 4 * lane) : make_uint2(0u, 0u);
         }
         float sd[BATCH];
 #pragma unroll
@@ -247,6 +262,13 @@ __global__ void __launch_bounds__(CH_ATT_THREADS) cham_attn_kernel(const float *
             for (int u = 0; u < BATCH; u++)
                 if (j0 + 8 * u < nk) sc[j0 + 8 * u] = sd[u] * scale;
         }
+    }
+    // the first round of V rows is requested now: it lands while the softmax statistics are reduced
+    uint2 vraw[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) {
+        const int j = warp + 8 * u;
+        vraw[u] = j < p ? *reinterpret_cast<const uint2 *>(V + (size_t)j * HD + 4 * lane) : make_uint2(0u, 0u);
     }
     __syncthreads();
     float m = -INFINITY;
@@ -277,9 +299,12 @@ __global__ void __launch_bounds__(CH_ATT_THREADS) cham_attn_kernel(const float *
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             const int j = j0 + 8 * u;
-            if (j < p) v4[u] = ld4(V + (size_t)j * HD + 4 * lane);
-            else if (j == p) v4[u] = *reinterpret_cast<const float4 *>(sv + 4 * lane);
-            else v4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v4[u] = j == p ? *reinterpret_cast<const float4 *>(sv + 4 * lane) : cvt4(vraw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + 8 * BATCH + 8 * u;
+            vraw[u] = j < p ? *reinterpret_cast<const uint2 *>(V + (size_t)j * HD + 4 * lane) : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
