@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(256) cham_embed_kernel(const ChamCall *cp, con
 }
 
 // One CTA per (q head, row).  qk LayerNorm, RoPE at the row's position, cache append (by the first q head of each kv
-// group), attention over keys 0..p.  head_dim 128: one warp covers a key with one 8-byte (4 x bf16) load per lane.
-__global__ void __launch_bounds__(CH_ATT_THREADS) cham_attn_kernel(const float *__restrict__ qkv, int ld_qkv, int H, int Hkv, int T,
+// group), attention over keys 0..p.  head_dim 128: sixteen lanes cover a key (one 16-byte load = 8 dims per lane), K and V loops software-pipelined.
+__global__ void __launch_bounds__(CH_ATT_THREADS, 4) cham_attn_kernel(const float *__restrict__ qkv, int ld_qkv, int H, int Hkv, int T,
                                                                    int qk_norm, float theta,
                                                                    const float *__restrict__ qn_g, const float *__restrict__ qn_b,
                                                                    const float *__restrict__ kn_g, const float *__restrict__ kn_b,
@@ -219,56 +219,64 @@ __global__ void __launch_bounds__(CH_ATT_THREADS) cham_attn_kernel(const float *
     __syncthreads();
     const float scale = 1.0f / sqrtf((float)HD);
     const int nk = p + 1;
-    const float4 q4 = *reinterpret_cast<const float4 *>(sq + 4 * lane);
-    auto ld4 = [&](const __nv_bfloat16 *ptr) {
-        const uint2 u = *reinterpret_cast<const uint2 *>(ptr);
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&u.x), b = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
-        return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+    // SIXTEEN lanes per key: a lane owns 8 consecutive dims (one 16-byte load of a bf16 cache row), a warp instruction
+    // covers TWO keys (half = lane >> 4), a round of BATCH instructions 16 keys per warp = 128 keys per CTA; the dot
+    // product needs 4 shuffle steps.  Twice the bytes in flight per load instruction of the 32-lane layout.
+    const int half = lane >> 4, l16 = lane & 15;
+    float q8[8];
+    {
+        const float4 qa = *reinterpret_cast<const float4 *>(sq + 8 * l16), qb = *reinterpret_cast<const float4 *>(sq + 8 * l16 + 4);
+        q8[0] = qa.x; q8[1] = qa.y; q8[2] = qa.z; q8[3] = qa.w; q8[4] = qb.x; q8[5] = qb.y; q8[6] = qb.z; q8[7] = qb.w;
+    }
+    constexpr int BATCH = 8, ROUND = 16 * BATCH;      // keys per CTA per round: 8 warps x 2 halves x BATCH
+    auto cvt8 = [&](const uint4 u, float (&f)[8]) {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) { f[2 * e] = __uint_as_float(w[e] << 16); f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
     };
-    constexpr int BATCH = 8;
-    auto cvt4 = [&](const uint2 u) {
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&u.x), b = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
-        return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+    auto own8 = [&](const float *src, float (&f)[8]) {
+        const float4 a4 = *reinterpret_cast<const float4 *>(src + 8 * l16), b4 = *reinterpret_cast<const float4 *>(src + 8 * l16 + 4);
+        f[0] = a4.x; f[1] = a4.y; f[2] = a4.z; f[3] = a4.w; f[4] = b4.x; f[5] = b4.y; f[6] = b4.z; f[7] = b4.w;
     };
-    // software pipeline: the 8 key rows of the NEXT round are requested before this round's dot products and shuffle
-    // reductions (at 1000 keys the kernel is a 260 MB stream per layer; load -> wait -> reduce -> load ran it at ~2 TB/s)
-    uint2 kraw[BATCH];
+    const int jw = 2 * warp + half;                    // this half-warp's first key; its keys: jw + 16 u + ROUND * round
+    // software pipeline: the rows of the NEXT round are requested before this round's dot products and shuffle reductions
+    uint4 kraw[BATCH];
 #pragma unroll
     for (int u = 0; u < BATCH; u++) {
-        const int j = warp + 8 * u;
-        kraw[u] = j < p ? *reinterpret_cast<const uint2 *>(K + (size_t)j * HD + 4 * lane) : make_uint2(0u, 0u);
+        const int j = jw + 16 * u;
+        kraw[u] = j < p ? *reinterpret_cast<const uint4 *>(K + (size_t)j * HD + 8 * l16) : make_uint4(0u, 0u, 0u, 0u);
     }
-    for (int j0 = warp; j0 < nk; j0 += 8 * BATCH) {
-        float4 k4[BATCH];
-#pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const int j = j0 + 8 * u;
-            k4[u] = j == p ? *reinterpret_cast<const float4 *>(sk + 4 * lane) : cvt4(kraw[u]);   // j == p: this pass's own key
-        }
-#pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const int j = j0 + 8 * BATCH + 8 * u;
-            kraw[u] = j < p ? *reinterpret_cast<const uint2 *>(K + (size_t)j * HD + 4 * lane) : make_uint2(0u, 0u);
-        }
+    for (int j0 = 0; j0 < nk; j0 += ROUND) {          // block-uniform trip count: the shuffles below use the full mask
         float sd[BATCH];
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) sd[u] = q4.x * k4[u].x + q4.y * k4[u].y + q4.z * k4[u].z + q4.w * k4[u].w;
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + jw + 16 * u;
+            float k8[8];
+            if (j == p) own8(sk, k8);                  // this pass's own key
+            else cvt8(kraw[u], k8);
+            const int jn = j + ROUND;                  // slot u is free again: request its row of the next round
+            kraw[u] = jn < p ? *reinterpret_cast<const uint4 *>(K + (size_t)jn * HD + 8 * l16) : make_uint4(0u, 0u, 0u, 0u);
+            float d = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+            for (int e = 0; e < 8; e++) d = fmaf(q8[e], k8[e], d);
+            sd[u] = d;
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
             for (int u = 0; u < BATCH; u++) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], o);
-        if (lane == 0) {
+        if (l16 == 0) {
 #pragma unroll
             for (int u = 0; u < BATCH; u++)
-                if (j0 + 8 * u < nk) sc[j0 + 8 * u] = sd[u] * scale;
+                if (j0 + jw + 16 * u < nk) sc[j0 + jw + 16 * u] = sd[u] * scale;
         }
     }
     // the first round of V rows is requested now: it lands while the softmax statistics are reduced
-    uint2 vraw[BATCH];
+    uint4 vraw[BATCH];
 #pragma unroll
     for (int u = 0; u < BATCH; u++) {
-        const int j = warp + 8 * u;
-        vraw[u] = j < p ? *reinterpret_cast<const uint2 *>(V + (size_t)j * HD + 4 * lane) : make_uint2(0u, 0u);
+        const int j = jw + 16 * u;
+        vraw[u] = j < p ? *reinterpret_cast<const uint4 *>(V + (size_t)j * HD + 8 * l16) : make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
     float m = -INFINITY;
@@ -293,27 +301,28 @@ __global__ void __launch_bounds__(CH_ATT_THREADS) cham_attn_kernel(const float *
 #pragma unroll
     for (int w = 0; w < 8; w++) sum += red[w];
     const float inv = 1.0f / sum;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j0 = warp; j0 < nk; j0 += 8 * BATCH) {
-        float4 v4[BATCH];
+    float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j0 = 0; j0 < nk; j0 += ROUND) {
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
-            const int j = j0 + 8 * u;
-            v4[u] = j == p ? *reinterpret_cast<const float4 *>(sv + 4 * lane) : cvt4(vraw[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const int j = j0 + 8 * BATCH + 8 * u;
-            vraw[u] = j < p ? *reinterpret_cast<const uint2 *>(V + (size_t)j * HD + 4 * lane) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const int j = j0 + 8 * u;
+            const int j = j0 + jw + 16 * u;
+            float v8[8];
+            if (j == p) own8(sv, v8);
+            else cvt8(vraw[u], v8);
+            const int jn = j + ROUND;
+            vraw[u] = jn < p ? *reinterpret_cast<const uint4 *>(V + (size_t)jn * HD + 8 * l16) : make_uint4(0u, 0u, 0u, 0u);
             const float pr = j < nk ? sc[j] * inv : 0.f;
-            acc.x += pr * v4[u].x; acc.y += pr * v4[u].y; acc.z += pr * v4[u].z; acc.w += pr * v4[u].w;
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc8[e] = fmaf(pr, v8[e], acc8[e]);
         }
     }
-    *reinterpret_cast<float4 *>(&part[warp][4 * lane]) = acc;
+    // the two halves of a warp hold different keys of the same dims
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc8[e] += __shfl_xor_sync(0xffffffffu, acc8[e], 16);
+    if (half == 0) {
+        *reinterpret_cast<float4 *>(&part[warp][8 * l16]) = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
+        *reinterpret_cast<float4 *>(&part[warp][8 * l16 + 4]) = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
+    }
     __syncthreads();
     if (tid < HD) {
         float o = 0.f;
