@@ -40,6 +40,11 @@ struct ConvTcArgs {
     int tiles_x, tiles_y;    // W / bw, H / bh
     int stride, pad;         // bf16 kernel only: 1 / 1 (same conv) or 2 / 0 (downsample conv: pad (0,1,0,1) = TMA zero fill
                              // past the right / bottom edge, model.py:69-72); H, W are the OUTPUT dims
+    // bf16 kernel only: GroupNorm(32) statistics of the OUTPUT tensor from the epilogue (the consumer is a GroupNorm):
+    // gn_out[(b * tiles_per_image + tile) * 32 + group] = (sum, sum of squares) over the tile's 128 pixels x the group's
+    // channels; a (tile, 128-channel block) writes exactly the groups its block covers -> no atomics, fixed summation order
+    double2 *gn_out;         // null: off
+    int gn_cg;               // channels per group = Cout / 32 (4, 8 or 16)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap *m, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -225,7 +230,8 @@ constexpr int CB_TMEM_A0 = 256;               // cols [0,128) accumulator 0, [12
 constexpr int CB_SM_BAR = CB_NS * CB_STAGE_BYTES;
 constexpr int CB_N_BARS = 2 * CB_NS + 2 * CB_NTA + 4;
 constexpr int CB_SM_MISC = CB_SM_BAR + 8 * CB_N_BARS;
-constexpr int CB_SM_BYTES = CB_SM_MISC + 16;
+constexpr int CB_SM_GN = CB_SM_MISC + 16;         // [4 epilogue warps][32 groups][2] floats of the GroupNorm epilogue
+constexpr int CB_SM_BYTES = CB_SM_GN + 4 * 32 * 2 * 4;
 constexpr int CB_SM_ALLOC = CB_SM_BYTES + 1024;
 static_assert(CB_SM_ALLOC <= 232448, "conv_tc bf16 kernel exceeds 227 KB of shared memory");
 
@@ -402,8 +408,13 @@ conv3x3_tc_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             const uint32_t acc = t_lane + (uint32_t)(it & 1) * 128u;
             mbar_wait_warp(acc_full(it & 1), (it >> 1) & 1, lane);
             fence_after_sync();
-#pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            float gsum[32], gsq[32];                  // (only live when a.gn_out != nullptr; indexed by compile-time constants)
+#pragma unroll
+            for (int gI = 0; gI < 32; gI++) { gsum[gI] = 0.f; gsq[gI] = 0.f; }
+            const int gshift = a.gn_cg == 4 ? 0 : (a.gn_cg == 8 ? 1 : 2);   // quads per group = 1, 2, 4
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const int c0 = cc * 32;
                 uint32_t d0[32];
                 tmem_ld32(acc + c0, d0);
                 wait_ld();
@@ -420,12 +431,48 @@ conv3x3_tc_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                         v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
                     }
                     *reinterpret_cast<float4 *>(dst + c0 + k) = v;
+                    if (a.gn_out != nullptr) {
+                        const float s1 = (v.x + v.y) + (v.z + v.w), s2 = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                        const int quad = cc * 8 + k / 4;          // compile-time: 0..31
+                        // group of this quad within the block: quad >> gshift; the three cases keep the index static
+                        if (gshift == 0) { gsum[quad] += s1; gsq[quad] += s2; }
+                        else if (gshift == 1) { gsum[quad >> 1] += s1; gsq[quad >> 1] += s2; }
+                        else { gsum[quad >> 2] += s1; gsq[quad >> 2] += s2; }
+                    }
                 }
             }
             // every TMEM read of this accumulator has completed (wait_ld above): hand it back to the MMA issuer
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(it & 1));
+            if (a.gn_out != nullptr) {
+                // GroupNorm statistics of this tile: gsum / gsq hold, per lane (= pixel), the sums over the channels of each
+                // group of this 128-channel block; reduce over the warp's 32 pixels, then over the 4 warps in warp order
+                const int ng = 128 / a.gn_cg;                              // groups in this block: 32, 16 or 8
+                float *gs = reinterpret_cast<float *>(smem + CB_SM_GN) + q * 64;
+#pragma unroll
+                for (int gI = 0; gI < 32; gI++) {
+                    if (gI >= ng) break;                                   // (warp-uniform)
+                    float s1 = gsum[gI], s2 = gsq[gI];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    }
+                    if (lane == 0) { gs[2 * gI] = s1; gs[2 * gI + 1] = s2; }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+                const int et = (warp - CT_W_EPI) * 32 + lane;              // 0..127
+                if (et < ng) {
+                    const float *g0 = reinterpret_cast<const float *>(smem + CB_SM_GN);
+                    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) { d1 += (double)g0[w * 64 + 2 * et]; d2 += (double)g0[w * 64 + 2 * et + 1]; }
+                    const int pt = tile / tl.nblk, bimg = pt / tpi, tin = pt - bimg * tpi;
+                    a.gn_out[((size_t)bimg * tpi + tin) * 32 + n0 / a.gn_cg + et] = make_double2(d1, d2);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");            // gs is reused by the next tile
+            }
         }
     }
 

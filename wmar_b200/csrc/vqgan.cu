@@ -41,6 +41,8 @@ struct Op {
     const float *gamma, *beta;
     int swish, H, W, C;
     int direct_in;    // conv: encoder conv_in on conv_in3_kernel, straight from the caller's NCHW image
+    int gn_emit;      // conv (bf16 tcgen05 path): the epilogue emits the GroupNorm statistics of its output (per-tile partials)
+    int from_conv;    // gn: statistics come from the producing conv's epilogue (gn_finalize_kernel instead of gn_partial_kernel)
     int stats_only;   // gn: only the statistics pass runs, the consumer (conv_out3_kernel) normalises while staging
     int fused_gn;
     // attn: q,k,v buffers
@@ -66,6 +68,7 @@ struct wmar_vqgan {
     size_t buf_floats;
     float *dots, *zz, *ee;
     double2 *gn_partial;
+    double2 *gn_tile = nullptr;   // [max_batch][R * R / 128][32] per-tile GroupNorm partials written by the conv epilogues
     double flops_enc, flops_dec;
     int enc_out_buf, latent;  // buffer holding the encoder output (pre-quant z), latent side
     const float *enc_images = nullptr;   // NCHW images of the running encode call (conv_in3_kernel reads them)
@@ -329,6 +332,8 @@ int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
     CUtensorMap mA, mWh, mWl;
     int rc;
     a.stride = o.stride; a.pad = o.stride == 2 ? 0 : 1;
+    a.gn_out = (o.gn_emit && o.wb1 != nullptr) ? v->gn_tile : nullptr;
+    a.gn_cg = o.Cout / 32;
     if ((rc = tc_nhwc_map(src, B, o.stride * o.Ho, o.stride * o.Wo, o.Cin, a.bw, a.bh, &mA, o.stride))) return rc;
     if (o.wb1 != nullptr) {
         // bf16x3: persistent kernel, one CTA per SM walking the (pixel tile, 128-channel block) list
@@ -377,7 +382,7 @@ int run_conv(const wmar_vqgan *v, const Op &o, int B, float *final_out, cudaStre
         ConvOutArgs a{};
         a.x = v->buf[o.src]; a.w = o.w; a.bias = o.b; a.out = final_out;
         a.H = o.Ho; a.W = o.Wo; a.C = o.C;
-        a.gn_partial = v->gn_partial; a.nchunk = gn_chunks(o.Ho * o.Wo, o.C);
+        a.gn_partial = v->gn_partial; a.nchunk = o.from_conv ? 1 : gn_chunks(o.Ho * o.Wo, o.C);   // (from_conv copied from its GroupNorm)
         a.gamma = o.gamma; a.beta = o.beta; a.eps = 1e-6f;
         a.out_scale = 1.f; a.out_shift = 0.f; a.clamp_lo = -1.f; a.clamp_hi = 1.f;
         if (v->cfg.family == 1) { a.clamp_lo = 0.f; a.clamp_hi = 1.f; a.out_scale = 2.f; a.out_shift = -1.f; }
@@ -422,8 +427,9 @@ int run_ops(const wmar_vqgan *v, const std::vector<Op> &ops, int B, float *final
                 if ((rc = run_conv(v, o, B, final_out, s))) return rc;
                 break;
             case OP_GN: {
-                const int HW = o.H * o.W, nchunk = gn_chunks(HW, o.C);
-                gn_partial_kernel<<<dim3(nchunk, B), GN_THREADS, 0, s>>>(v->buf[o.src], HW, o.C, nchunk, v->gn_partial);
+                const int HW = o.H * o.W, nchunk = o.from_conv ? 1 : gn_chunks(HW, o.C);
+                if (o.from_conv) gn_finalize_kernel<<<B, 256, 0, s>>>(v->gn_tile, HW / 128, v->gn_partial);
+                else gn_partial_kernel<<<dim3(nchunk, B), GN_THREADS, 0, s>>>(v->buf[o.src], HW, o.C, nchunk, v->gn_partial);
                 WMAR_LAUNCH_CHECK();
                 if (o.stats_only) break;
                 long long total4 = (long long)HW * o.C / 4;
@@ -515,6 +521,34 @@ int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights
                 }
             }
     }
+    // GroupNorm statistics from the producing conv's epilogue (WMAR_GN_FUSE=0: always the separate statistics pass): a
+    // GroupNorm whose input was written by a conv on the persistent bf16 tcgen05 kernel (whole output = that conv's tiles)
+    {
+        const char *e = getenv("WMAR_GN_FUSE");
+        const bool fuse = !(e && e[0] == '0');
+        WMAR_CUDA_CHECK(cudaMalloc(&v->gn_tile, sizeof(double2) * 32 * (size_t)cfg->max_batch * ((size_t)R * R / 128)));
+        for (auto *ops : {&v->enc, &v->dec})
+            for (size_t i = 0; fuse && i < ops->size(); i++) {
+                Op &gn = (*ops)[i];
+                if (gn.kind != OP_GN) continue;
+                int p = -1;                      // the most recent writer of the GroupNorm's input buffer
+                for (int k = (int)i - 1; k >= 0 && p < 0; k--) {
+                    const Op &w = (*ops)[k];
+                    const bool writes = (w.kind == OP_CONV && !w.final_out && w.dst == gn.src) || (w.kind != OP_CONV && w.dst == gn.src);
+                    if (writes) p = k;
+                }
+                if (p < 0) continue;
+                Op &cv = (*ops)[p];
+                if (cv.kind != OP_CONV || cv.wb1 == nullptr || cv.Cout != gn.C || cv.Ho != gn.H || cv.Wo != gn.W) continue;
+                if ((cv.Ho * cv.Wo) % 128 != 0) continue;
+                bool clash = false;              // no other emitting conv between producer and consumer (one statistics buffer)
+                for (size_t k = (size_t)p + 1; k < i; k++) clash |= (*ops)[k].kind == OP_CONV && (*ops)[k].gn_emit;
+                if (clash) continue;
+                cv.gn_emit = 1;
+                gn.from_conv = 1;
+                if (gn.stats_only && i + 1 < ops->size()) (*ops)[i + 1].from_conv = 1;   // the fused decoder-tail conv reads nchunk = 1
+            }
+    }
     const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -544,7 +578,7 @@ void wmar_vqgan_destroy(wmar_vqgan *v) {
     cudaFree(v->dots); cudaFree(v->zz); cudaFree(v->ee); cudaFree(v->gn_partial);
     for (cudaGraphExec_t e : v->dec_exec) if (e) cudaGraphExecDestroy(e);
     for (cudaGraphExec_t e : v->enc_exec) if (e) cudaGraphExecDestroy(e);
-    cudaFree(v->g_codes); cudaFree(v->g_images);
+    cudaFree(v->g_codes); cudaFree(v->g_images); cudaFree(v->gn_tile);
     delete v;
 }
 

@@ -67,6 +67,27 @@ __global__ void __launch_bounds__(GN_THREADS) gn_partial_kernel(const float *__r
     (void)sh; (void)grp;
 }
 
+// Stage 1': the statistics came from the producing conv's epilogue as per-tile partials [B][tiles][32] (conv_tc.cuh): sum
+// them in a fixed order into the [B][1][32] layout stage 2 reads with nchunk = 1.  grid B, 256 threads.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const double2 *__restrict__ tile_partial, int tiles,
+                                                          double2 *__restrict__ partial) {
+    __shared__ double2 sh[8][32];
+    const int b = blockIdx.x, g = threadIdx.x & 31, part = threadIdx.x >> 5;
+    double a0 = 0.0, a1 = 0.0;
+    for (int t = part; t < tiles; t += 8) {
+        const double2 p = tile_partial[((size_t)b * tiles + t) * 32 + g];
+        a0 += p.x; a1 += p.y;
+    }
+    sh[part][g] = make_double2(a0, a1);
+    __syncthreads();
+    if (part == 0) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { s0 += sh[k][g].x; s1 += sh[k][g].y; }
+        partial[(size_t)b * 32 + g] = make_double2(s0, s1);
+    }
+}
+
 // Stage 2: y = act((x - mean_g) * rstd_g * gamma_c + beta_c); act = swish (x*sigmoid(x)) or identity.
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float *__restrict__ x, float *__restrict__ y, int HW, int C,
                                                        int nchunk, const double2 *__restrict__ partial,
