@@ -38,6 +38,7 @@ struct ConvTcArgs {
     int H, W, Cin, Cout;     // Cin = padded input channels (multiple of 32), Cout = real output channels (multiple of 128)
     int bw, bh;              // pixel tile: bw x bh = 128
     int tiles_x, tiles_y;    // W / bw, H / bh
+    int taps;                // 9 (3x3) or 1 (1x1 conv / plain GEMM over "pixels"); 0 is read as 9
     int stride, pad;         // bf16 kernel only: 1 / 1 (same conv) or 2 / 0 (downsample conv: pad (0,1,0,1) = TMA zero fill
                              // past the right / bottom edge, model.py:69-72); H, W are the OUTPUT dims
     // bf16 kernel only: GroupNorm(32) statistics of the OUTPUT tensor from the epilogue (the consumer is a GroupNorm):
@@ -66,7 +67,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int b = blockIdx.x / tpi, tr = blockIdx.x - b * tpi;
     const int ty = tr / a.tiles_x, tx = tr - ty * a.tiles_x;
     const int x0 = tx * a.bw, y0 = ty * a.bh, n0 = blockIdx.y * 128;
-    const int cchunks = a.Cin / 32, nchunks = 9 * cchunks;
+    const int taps = a.taps == 1 ? 1 : 9, off = a.taps == 1 ? 0 : 1;
+    const int cchunks = a.Cin / 32, nchunks = taps * cchunks;
 
     const uint32_t bar0 = smem_base + CT_SM_BAR;
     auto s_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -102,7 +104,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 mbar_wait(s_empty(s), ((c / CT_NS) & 1) ^ 1);
                 mbar_arrive_expect_tx(s_full(s), CT_STAGE_BYTES);
                 const uint32_t dst = smem_base + s * CT_STAGE_BYTES;
-                tma_load_4d(dst, &mapA, ci0, x0 + kx - 1, y0 + ky - 1, b, s_full(s));           // zero fill = padding
+                tma_load_4d(dst, &mapA, ci0, x0 + kx - off, y0 + ky - off, b, s_full(s));       // zero fill = padding
                 tma_load_2d(dst + CT_TILE_BYTES, &mapWh, tap * a.Cin + ci0, n0, s_full(s), L2_EVICT_LAST);
                 tma_load_2d(dst + 2 * CT_TILE_BYTES, &mapWl, tap * a.Cin + ci0, n0, s_full(s), L2_EVICT_LAST);
             }
@@ -269,7 +271,7 @@ conv3x3_tc_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     uint8_t *smem = ct_smem_raw + (smem_base - smem_u32(ct_smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tpi = a.tiles_x * a.tiles_y;
-    const int cchunks = a.Cin / 64, nchunks = 9 * cchunks;
+    const int cchunks = a.Cin / 64, nchunks = (a.taps == 1 ? 1 : 9) * cchunks;
 
     const uint32_t bar0 = smem_base + CB_SM_BAR;
     auto s_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };

@@ -68,6 +68,7 @@ struct wmar_vqgan {
     size_t buf_floats;
     float *dots, *zz, *ee;
     double2 *gn_partial;
+    float *cb_lo = nullptr, *zero_bias = nullptr;   // codebook - trunc_tf32(codebook), zeros[n_embed]: distance GEMM on the tcgen05 kernel
     double2 *gn_tile = nullptr;   // [max_batch][R * R / 128][32] per-tile GroupNorm partials written by the conv epilogues
     double flops_enc, flops_dec;
     int enc_out_buf, latent;  // buffer holding the encoder output (pre-quant z), latent side
@@ -295,6 +296,15 @@ bool conv_tc_s2_eligible(const Op &o) {
     return 128 % o.Wo == 0 && o.Ho % (128 / o.Wo) == 0;
 }
 
+// 1x1 convs (attention q / k / v / proj_out, nin_shortcut, quant / post_quant convs) on the bf16x3 tcgen05 kernel: one tap
+bool conv_tc_1x1_eligible(const Op &o) {
+    if (o.ks != 1 || o.stride != 1 || o.pad != 0 || o.final_out || o.up) return false;
+    if (o.C != o.Cin || o.Cin % 64 != 0 || o.Cout % 128 != 0 || o.Cout != o.Cout_pad) return false;
+    if (o.Ho != o.Hs || o.Wo != o.Ws || o.Wo < 8) return false;
+    if (o.Wo >= 128) return o.Wo % 128 == 0;
+    return 128 % o.Wo == 0 && o.Ho % (128 / o.Wo) == 0;
+}
+
 // nearest x2 (taming model.py:39-54 Upsample: F.interpolate(scale_factor=2, mode="nearest")), NHWC, 16-byte vectors
 __global__ void upsample2x_nhwc_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int B, int H, int W, int C4) {
     const size_t n = (size_t)B * 2 * H * 2 * W * C4;
@@ -331,7 +341,9 @@ int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
     a.tiles_x = o.Wo / a.bw; a.tiles_y = o.Ho / a.bh;
     CUtensorMap mA, mWh, mWl;
     int rc;
-    a.stride = o.stride; a.pad = o.stride == 2 ? 0 : 1;
+    a.taps = o.ks == 1 ? 1 : 9;
+    a.stride = o.stride; a.pad = (o.ks == 3 && o.stride == 1) ? 1 : 0;
+    const int Kw = o.ks * o.ks * o.Cin;      // row length of the [Cout][ky][kx][Cin] weights
     a.gn_out = (o.gn_emit && o.wb1 != nullptr) ? v->gn_tile : nullptr;
     a.gn_cg = o.Cout / 32;
     if ((rc = tc_nhwc_map(src, B, o.stride * o.Ho, o.stride * o.Wo, o.Cin, a.bw, a.bh, &mA, o.stride))) return rc;
@@ -342,8 +354,8 @@ int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
             WMAR_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SM_ALLOC));
             configured_b = true;
         }
-        if ((rc = tc_weight_map_bf16(o.wb1, o.Cout_pad, 9 * o.Cin, &mWh))) return rc;
-        if ((rc = tc_weight_map_bf16(o.wb2, o.Cout_pad, 9 * o.Cin, &mWl))) return rc;
+        if ((rc = tc_weight_map_bf16(o.wb1, o.Cout_pad, Kw, &mWh))) return rc;
+        if ((rc = tc_weight_map_bf16(o.wb2, o.Cout_pad, Kw, &mWl))) return rc;
         ConvTcTiles tl{};
         tl.nblk = o.Cout / 128;
         tl.n_tiles = B * a.tiles_x * a.tiles_y * tl.nblk;
@@ -355,8 +367,8 @@ int run_conv_tc(const wmar_vqgan *v, const Op &o, int B, cudaStream_t s) {
         WMAR_LAUNCH_CHECK();
         return WMAR_OK;
     }
-    if ((rc = tc_weight_map(o.w, o.Cout_pad, 9 * o.Cin, &mWh))) return rc;
-    if ((rc = tc_weight_map(o.wlo, o.Cout_pad, 9 * o.Cin, &mWl))) return rc;
+    if ((rc = tc_weight_map(o.w, o.Cout_pad, Kw, &mWh))) return rc;
+    if ((rc = tc_weight_map(o.wlo, o.Cout_pad, Kw, &mWl))) return rc;
     dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)(o.Cout / 128));
     conv3x3_tc_kernel<<<grid, CT_THREADS, CT_SM_ALLOC, s>>>(mA, mWh, mWl, a);
     WMAR_LAUNCH_CHECK();
@@ -503,13 +515,21 @@ int wmar_vqgan_create(const wmar_vqgan_config *cfg, const void *const *d_weights
     {
         const char *e = getenv("WMAR_CONV");
         const bool want_tc = !(e && e[0] == 'v') && tc_available();
+        if (want_tc) {
+            const size_t ncb = (size_t)cfg->n_embed * cfg->embed_dim;
+            WMAR_CUDA_CHECK(cudaMalloc(&v->cb_lo, sizeof(float) * ncb));
+            conv_tc_wlo_kernel<<<1024, 256>>>(v->codebook, v->cb_lo, ncb);
+            WMAR_LAUNCH_CHECK();
+            WMAR_CUDA_CHECK(cudaMalloc(&v->zero_bias, sizeof(float) * cfg->n_embed));
+            WMAR_CUDA_CHECK(cudaMemset(v->zero_bias, 0, sizeof(float) * cfg->n_embed));
+        }
         for (auto *ops : {&v->enc, &v->dec})
             for (Op &o : *ops) {
                 o.wlo = nullptr;
                 const bool bf = cfg->precision == 2 || (cfg->precision == 3 && ops == &v->dec);
-                const bool s2 = bf && o.kind == OP_CONV && conv_tc_s2_eligible(o);
+                const bool s2 = bf && o.kind == OP_CONV && (conv_tc_s2_eligible(o) || conv_tc_1x1_eligible(o));   // bf16 kernel only
                 if (!want_tc || o.kind != OP_CONV || o.direct_in || !(conv_tc_eligible(o) || s2)) continue;
-                const size_t nw = (size_t)o.Cout_pad * 9 * o.Cin;
+                const size_t nw = (size_t)o.Cout_pad * o.ks * o.ks * o.Cin;
                 WMAR_CUDA_CHECK(cudaMalloc(&o.wlo, sizeof(float) * nw));   // (also the "tcgen05 path" marker of run_conv)
                 conv_tc_wlo_kernel<<<1024, 256>>>(o.w, o.wlo, nw);
                 WMAR_LAUNCH_CHECK();
@@ -578,7 +598,7 @@ void wmar_vqgan_destroy(wmar_vqgan *v) {
     cudaFree(v->dots); cudaFree(v->zz); cudaFree(v->ee); cudaFree(v->gn_partial);
     for (cudaGraphExec_t e : v->dec_exec) if (e) cudaGraphExecDestroy(e);
     for (cudaGraphExec_t e : v->enc_exec) if (e) cudaGraphExecDestroy(e);
-    cudaFree(v->g_codes); cudaFree(v->g_images); cudaFree(v->gn_tile);
+    cudaFree(v->g_codes); cudaFree(v->g_images); cudaFree(v->gn_tile); cudaFree(v->cb_lo); cudaFree(v->zero_bias);
     delete v;
 }
 
@@ -614,14 +634,29 @@ static int vqgan_encode_eager(wmar_vqgan *v, const float *d_images, int64_t B, i
     const float *z = v->buf[v->enc_out_buf];
     row_sumsq_kernel<<<(tokens + 7) / 8, 256, 0, s>>>(z, v->zz, tokens, D);
     WMAR_LAUNCH_CHECK();
-    ConvArgs a{};
-    a.in = z; a.w = v->codebook; a.bias = nullptr; a.resid = nullptr; a.out = v->dots;
-    a.B = 1; a.Hs = 1; a.Ws = tokens; a.Cin = D; a.Ho = 1; a.Wo = tokens; a.Cout = NE; a.Cout_pad = NE;
-    a.ks = 1; a.stride = 1; a.pad = 0; a.up = 0; a.out_scale = 1.f;
     WMAR_REQUIRE(tokens % CV_BM == 0, "token count must be a multiple of 128");
-    const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
-    conv_igemm_kernel<1><<<dim3(tokens / CV_BM, NE / CV_BN), CV_THREADS, smem, s>>>(a);
-    WMAR_LAUNCH_CHECK();
+    if (v->cb_lo != nullptr && D % 32 == 0 && NE % 128 == 0) {
+        // tcgen05 3xTF32 kernel as a plain GEMM: the tokens are a 1 x tokens "image", one tap (always fp32-faithful 3xTF32:
+        // the arg-min decides ties at fp32 rounding distance, whatever the precision of the conv stacks)
+        ConvTcArgs t{};
+        t.bias = v->zero_bias; t.resid = nullptr; t.out = v->dots;
+        t.H = 1; t.W = tokens; t.Cin = D; t.Cout = NE; t.bw = 128; t.bh = 1; t.tiles_x = tokens / 128; t.tiles_y = 1; t.taps = 1;
+        CUtensorMap mA, mWh, mWl;
+        int rc2;
+        if ((rc2 = tc_nhwc_map(z, 1, 1, tokens, D, 128, 1, &mA))) return rc2;
+        if ((rc2 = tc_weight_map(v->codebook, NE, D, &mWh))) return rc2;
+        if ((rc2 = tc_weight_map(v->cb_lo, NE, D, &mWl))) return rc2;
+        conv3x3_tc_kernel<<<dim3((unsigned)(tokens / 128), (unsigned)(NE / 128)), CT_THREADS, CT_SM_ALLOC, s>>>(mA, mWh, mWl, t);
+        WMAR_LAUNCH_CHECK();
+    } else {
+        ConvArgs a{};
+        a.in = z; a.w = v->codebook; a.bias = nullptr; a.resid = nullptr; a.out = v->dots;
+        a.B = 1; a.Hs = 1; a.Ws = tokens; a.Cin = D; a.Ho = 1; a.Wo = tokens; a.Cout = NE; a.Cout_pad = NE;
+        a.ks = 1; a.stride = 1; a.pad = 0; a.up = 0; a.out_scale = 1.f;
+        const size_t smem = sizeof(float) * 2 * (CV_BM + CV_BN) * CV_LD;
+        conv_igemm_kernel<1><<<dim3(tokens / CV_BM, NE / CV_BN), CV_THREADS, smem, s>>>(a);
+        WMAR_LAUNCH_CHECK();
+    }
     vq_argmin_kernel<<<tokens, 256, 0, s>>>(v->dots, v->zz, v->ee, d_codes, NE);
     WMAR_LAUNCH_CHECK();
     return WMAR_OK;
