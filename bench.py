@@ -408,8 +408,10 @@ def run_taming(args, rank, world, dev, L, peaks):
         # cache / scratch / step graph, shared weights; taming_wrapper.py sample()).  A step here = 2 x B images.
         model.lanes = args.lanes
         cond2 = [CLASSES[(rank * B + i) % len(CLASSES)] for i in range(args.lanes * B)]
-        m2 = measure_generation(args, world, dev, model, wm, cond2, GEN_PARAMS, steps_tok, L)
-        b2 = generation_block(args, world, args.lanes * B, steps_tok, m2, args.lanes * model._gpt.algorithmic_bytes(B, steps_tok), peaks,
+        args2 = argparse.Namespace(**vars(args))      # an extra block: at most 4 timed steps after at most 3 warm-up steps
+        args2.steps, args2.warmup = min(args.steps, 4), min(args.warmup, 3)
+        m2 = measure_generation(args2, world, dev, model, wm, cond2, GEN_PARAMS, steps_tok, L)
+        b2 = generation_block(args2, world, args.lanes * B, steps_tok, m2, args.lanes * model._gpt.algorithmic_bytes(B, steps_tok), peaks,
                               f"{args.lanes} concurrent decode loops (each 256 token steps at {B} rows; every loop streams the weights itself)",
                               None)
         b2.update({"metric": METRIC.replace("batch 16/GPU", f"{args.lanes} concurrent batches of 16/GPU"), "dtype": blk["dtype"],
@@ -567,8 +569,10 @@ def run_rar_xl(args, rank, world, dev, L, peaks):
     if args.lanes > 1:
         model.lanes = args.lanes     # same wrapper call with lanes x 8 conditionings: concurrent engine lanes (see run_taming)
         cond2 = [RAR_CLASSES[(rank * B + i) % len(RAR_CLASSES)] for i in range(args.lanes * B)]
-        m2 = measure_generation(args, world, dev, model, wm, cond2, None, steps_tok, L)
-        b2 = generation_block(args, world, args.lanes * B, steps_tok, m2, args.lanes * model._rar.algorithmic_bytes(B, steps_tok), peaks,
+        args2 = argparse.Namespace(**vars(args))
+        args2.steps, args2.warmup = min(args.steps, 4), min(args.warmup, 3)
+        m2 = measure_generation(args2, world, dev, model, wm, cond2, None, steps_tok, L)
+        b2 = generation_block(args2, world, args.lanes * B, steps_tok, m2, args.lanes * model._rar.algorithmic_bytes(B, steps_tok), peaks,
                               f"{args.lanes} concurrent RAR decode loops (each 256 guided passes over 16 rows; every loop streams the weights itself)",
                               None)
         b2.update({"metric": RAR_METRIC.replace("batch 8/GPU", f"{args.lanes} concurrent batches of 8/GPU"), "dtype": blk["dtype"],
