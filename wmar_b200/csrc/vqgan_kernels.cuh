@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(CO_T * CO_T) conv_out3_kernel(const ConvOutArg
 // K = 27, so as an implicit GEMM (input padded to 32 channels) 29/32 of the tensor work multiplies zeros (0.66 ms + 0.13 ms
 // for the NHWC repack per 16 images).  Here a CTA owns 32 x 2 output pixels: the 34 x 4 x 3 input halo and the
 // [27][Cout] weights sit in shared memory, a thread accumulates 8 pixels x 4 output channels in fp32 (exact products).
-constexpr int CI_TW = 32, CI_TH = 2;
+constexpr int CI_TW = 32, CI_TH = 8;   // 256 pixels per CTA: the 13.8 KB weight stage is amortised over four row pairs
 struct ConvInArgs {
     const float *img;        // NCHW [B][3][H][W]
     const float *w;          // [Cout][3][3][Cin_pad] (first 3 input channels real)
@@ -255,7 +255,7 @@ struct ConvInArgs {
     int H, W, Cout, Cin_pad;
     float scale, shift;      // v = x * scale + shift before the conv (RAR: (x+1)/2), padding stays zero
 };
-__global__ void __launch_bounds__(256) conv_in3_kernel(const ConvInArgs a) {
+__global__ void __launch_bounds__(256, 3) conv_in3_kernel(const ConvInArgs a) {
     extern __shared__ __align__(16) float ci_smem[];
     float *wsm = ci_smem;                                   // [27][Cout]
     float *xin = ci_smem + 27 * a.Cout;                     // [3][CI_TH + 2][CI_TW + 2]
@@ -270,35 +270,39 @@ __global__ void __launch_bounds__(256) conv_in3_kernel(const ConvInArgs a) {
         xin[i] = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? a.img[(((size_t)b * 3 + c) * a.H + gy) * a.W + gx] * a.scale + a.shift : 0.f;
     }
     __syncthreads();
-    const int pg = tid >> 5, py = pg >> 2, pxb = (pg & 3) * 8;         // 8 pixels of one row per warp
-    for (int n4 = (tid & 31) * 4; n4 < a.Cout; n4 += 128) {
-        float acc[8][4];
+    const int pg = tid >> 5, pxb = (pg & 3) * 8;                       // 8 pixels of one row per warp, two rows per round
+#pragma unroll 1
+    for (int rr = 0; rr < CI_TH / 2; rr++) {
+        const int py = 2 * rr + (pg >> 2);
+        for (int n4 = (tid & 31) * 4; n4 < a.Cout; n4 += 128) {
+            float acc[8][4];
 #pragma unroll
-        for (int p = 0; p < 8; p++)
+            for (int p = 0; p < 8; p++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) acc[p][e] = 0.f;
+                for (int e = 0; e < 4; e++) acc[p][e] = 0.f;
+#pragma unroll 3
+            for (int tap = 0; tap < 9; tap++) {
 #pragma unroll
-        for (int tap = 0; tap < 9; tap++) {
+                for (int c = 0; c < 3; c++) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(wsm + (tap * 3 + c) * a.Cout + n4);
+                    const float *xr = xin + (c * (CI_TH + 2) + py + tap / 3) * (CI_TW + 2) + pxb + tap % 3;
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const float4 w4 = *reinterpret_cast<const float4 *>(wsm + (tap * 3 + c) * a.Cout + n4);
-                const float *xr = xin + (c * (CI_TH + 2) + py + tap / 3) * (CI_TW + 2) + pxb + tap % 3;
-#pragma unroll
-                for (int p = 0; p < 8; p++) {
-                    const float xv = xr[p];
-                    acc[p][0] = fmaf(xv, w4.x, acc[p][0]); acc[p][1] = fmaf(xv, w4.y, acc[p][1]);
-                    acc[p][2] = fmaf(xv, w4.z, acc[p][2]); acc[p][3] = fmaf(xv, w4.w, acc[p][3]);
+                    for (int p = 0; p < 8; p++) {
+                        const float xv = xr[p];
+                        acc[p][0] = fmaf(xv, w4.x, acc[p][0]); acc[p][1] = fmaf(xv, w4.y, acc[p][1]);
+                        acc[p][2] = fmaf(xv, w4.z, acc[p][2]); acc[p][3] = fmaf(xv, w4.w, acc[p][3]);
+                    }
                 }
             }
-        }
-        const float4 b4 = *reinterpret_cast<const float4 *>(a.bias + n4);
-        const int gy = y0 + py;
+            const float4 b4 = *reinterpret_cast<const float4 *>(a.bias + n4);
+            const int gy = y0 + py;
 #pragma unroll
-        for (int p = 0; p < 8; p++) {
-            const int gx = x0 + pxb + p;
-            if (gy < a.H && gx < a.W)
-                *reinterpret_cast<float4 *>(a.out + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + n4) =
-                    make_float4(acc[p][0] + b4.x, acc[p][1] + b4.y, acc[p][2] + b4.z, acc[p][3] + b4.w);
+            for (int p = 0; p < 8; p++) {
+                const int gx = x0 + pxb + p;
+                if (gy < a.H && gx < a.W)
+                    *reinterpret_cast<float4 *>(a.out + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + n4) =
+                        make_float4(acc[p][0] + b4.x, acc[p][1] + b4.y, acc[p][2] + b4.z, acc[p][3] + b4.w);
+            }
         }
     }
 }
