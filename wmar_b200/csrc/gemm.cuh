@@ -5,13 +5,16 @@
 // with as many 16-byte loads in flight as possible and doing the math on the tensor pipe:
 //   * the 16 batch rows are exactly the M of mma.m16n8k8; W rows map to the MMA's n, and every lane fetches exactly
 //     the 16-byte pieces that are ITS B fragments (one piece covers two k8 steps of one n8 tile).  The pieces travel
-//     with cp.async through a per-warp, per-lane private shared-memory ring (3 stages x 4 KB per warp): shared memory
-//     is used purely as extra load-queue depth -- up to three iterations of every warp are in flight at once (96 KB
-//     per CTA, 192 KB per SM) instead of the two a register double buffer allows, and a lane only ever reads back what
-//     it wrote itself, so there is no barrier and no bank conflict,
+//     through a per-warp shared-memory ring (3 stages x 4 KB per warp): shared memory is used purely as extra load-queue
+//     depth -- up to three iterations of every warp are in flight at once (96 KB per CTA, 192 KB per SM) instead of the
+//     two a register double buffer allows, and a lane only ever reads back its own pieces, so there is no CTA barrier and
+//     no bank conflict.  The ring is filled by the TMA unit (default since round 2: one cp.async.bulk.tensor.2d box of
+//     16 k x 64 rows per warp iteration, completion on a per-(warp, stage) mbarrier) or by per-lane cp.async (round 1,
+//     WMAR_GEMM_LOAD=cpasync; measured equal -- the weight stream is not on the critical path),
 //   * products are 3xTF32 (hi*hi + hi*lo + lo*hi with fp32 accumulation): fp32-faithful results, which the
 //     reference's fp32 (TF32-off) Linear layers require for greedy token parity,
-//   * split-K across CTAs (grid.y) fills all 148 SMs even for N = 1536; partial tiles go to an L2-resident workspace
+//   * split-K across CTAs (grid.y) fills the 148 SMs even for N = 1536 -- tiles x splits is kept within ONE wave of the
+//     2 x 148 resident CTAs (pick_splits, gemm.cu), K is cut into near-equal parts; partial tiles go to an L2-resident workspace
 //     as {value, flag} words and the CTA of the last split sums them in split order (deterministic) and runs the
 //     epilogue -- no fence, no atomic (GemmArgs::ll_salt; the counter-based last-arriver hand-off is kept as ll_salt = 0),
 //   * LayerNorm / adaLN-modulate are applied to X on the fly (prologue) from per-row statistics that the producing

@@ -78,7 +78,7 @@ struct wmar_gpt {
     float *ws2;        // second partial buffer (MLP block)
     float *hpart;      // K-split partials of the fc1 tiles
     unsigned *hflag;   // [n_layer][4d/128] arrival counters
-    // persistent step kernel (pstep.cuh): the default path, one launch per token step instead of 5 per layer
+    // persistent step kernel (pstep.cuh): opt-in (WMAR_STEP=pstep, measured slower than the per-GEMM graph), one launch per token step
     PstepState *pstep;
     int *ticket;       // arrival counter of gpt_tail_kernel (self-resetting)
 };
