@@ -727,6 +727,17 @@ int wmar_gpt_create(const wmar_gpt_config *cfg, const void *const *d_weights, in
     g->splits_fc1 = pick_splits(4 * d, d, g->n_sms);
     g->splits_fc2 = pick_splits(d, 4 * d, g->n_sms);
     g->splits_head = pick_splits(V, d, g->n_sms);
+    {   // probe only: WMAR_SPLITS="qkv,proj,fc1,fc2,head" overrides (0 keeps the pick)
+        const char *e = getenv("WMAR_SPLITS");
+        int v5[5] = {0, 0, 0, 0, 0};
+        if (e && sscanf(e, "%d,%d,%d,%d,%d", &v5[0], &v5[1], &v5[2], &v5[3], &v5[4]) >= 1) {
+            if (v5[0] > 0) g->splits_qkv = v5[0];
+            if (v5[1] > 0) g->splits_proj = v5[1];
+            if (v5[2] > 0) g->splits_fc1 = v5[2];
+            if (v5[3] > 0) g->splits_fc2 = v5[3];
+            if (v5[4] > 0) g->splits_head = v5[4];
+        }
+    }
     size_t ws_floats = 0;
     auto upd = [&](int N, int K, int S) { size_t n = gemm_ws_floats(N, K, S, g->n_sms); if (n > ws_floats) ws_floats = n; };
     upd(3 * d, d, g->splits_qkv); upd(d, d, g->splits_proj); upd(4 * d, d, g->splits_fc1); upd(d, 4 * d, g->splits_fc2);
