@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--no-anole", action="store_true", help="skip the Anole-7B extra block (one ~7 s step + warm-up)")
-    ap.add_argument("--lanes", type=int, default=2, help="extra block: this many batches of 16 on concurrent engine lanes (1 = skip)")
+    ap.add_argument("--lanes", type=int, default=3, help="extra block: this many batches of 16 on concurrent engine lanes (1 = skip)")
     ap.add_argument("--vqgan-precision", choices=["3xtf32", "tf32", "bf16x3", "bf16x3-dec"], default="bf16x3")
     ap.add_argument("--rng", choices=["torch", "philox"], default="torch")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -147,7 +147,7 @@ def get_parser():
     p.add_argument("--num_samples_per_conditioning", type=int, default=1)
     p.add_argument("--conditioning", type=str)
     p.add_argument("--batch_size", type=int, nargs="?", default=10)
-    p.add_argument("--lanes", type=int, default=2,
+    p.add_argument("--lanes", type=int, default=3,
                    help="consecutive batches sampled concurrently on engine lanes of one GPU (1 = the reference's sequential loop)")
     p.add_argument("--top_k", type=int, nargs="?", default=600)
     p.add_argument("--temperature", type=float, nargs="?", default=1.0)

@@ -41,7 +41,7 @@ def _stand_in_tokenizer(prompt):
 
 class ChameleonARMMWrapper(AutoregressiveMultimodalModelWrapper):
     def __init__(self, modelpath=None, *, state_dict=None, tokenizer_state_dict=None, model_cfg=None, vq_cfg=None,
-                 tokenize=None, bpe2img=None, device="cuda", max_batch=8, vqgan_precision="bf16x3", seed=0, rng="torch", lanes=2,
+                 tokenize=None, bpe2img=None, device="cuda", max_batch=8, vqgan_precision="bf16x3", seed=0, rng="torch", lanes=3,
                  guidance_text=3.0, guidance_image=1.2, image_tokens_per_image=1024, alive_ids_path=None):
         super().__init__()
         self._device = torch.device(device)

@@ -20,7 +20,7 @@ ASSETS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 
 class RarARMMWrapper(AutoregressiveMultimodalModelWrapper):
     def __init__(self, modelpath=None, rar_size="rar_xl", *, state_dict=None, tokenizer_state_dict=None, rar_cfg=None,
-                 vq_cfg=None, device="cuda", max_batch=8, vqgan_precision="bf16x3", seed=0, alive_ids_path=None, lanes=2,
+                 vq_cfg=None, device="cuda", max_batch=8, vqgan_precision="bf16x3", seed=0, alive_ids_path=None, lanes=3,
                  rng="torch"):
         """modelpath: directory holding ``{rar_size}.bin`` and ``maskgit-vqgan-imagenet-f16-256.bin`` (the files the
         reference downloads, rar_wrapper.py:27-34); None -> seeded random-init weights at the ``rar_size`` shapes."""

@@ -38,7 +38,7 @@ def _load_net2net(modelpath):
 
 class TamingARMMWrapper(AutoregressiveMultimodalModelWrapper):
     def __init__(self, modelpath=None, *, state_dict=None, gpt_cfg=None, dd_cfg=None, device="cuda", max_batch=16,
-                 vqgan_precision="bf16x3", seed=0, alive_ids_path=None, rng="torch", lanes=2):
+                 vqgan_precision="bf16x3", seed=0, alive_ids_path=None, rng="torch", lanes=3):
         """modelpath: directory of the reference's Taming download (README.md); None -> seeded random-init weights at
         ``gpt_cfg`` / ``dd_cfg`` shapes (default: the reference's cin_transformer shapes), or an explicit
         ``state_dict`` with Net2NetTransformer keys.  rng: "torch" draws torch.multinomial's own CUDA Philox stream inside
