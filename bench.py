@@ -404,8 +404,8 @@ def run_taming(args, rank, world, dev, L, peaks):
                            "step_path": os.environ.get("WMAR_STEP", "default"),
                            "l2": "inputs larger than L2 (5.5 GB of weights streamed per token step)"}})
     if args.lanes > 1:
-        # the same wrapper call with 2 x B conditionings: two batches of B run concurrently on two engine lanes (own KV
-        # cache / scratch / step graph, shared weights; taming_wrapper.py sample()).  A step here = 2 x B images.
+        # the same wrapper call with lanes x B conditionings: the batches of B run concurrently on engine lanes (own KV
+        # cache / scratch / step graph, shared weights; taming_wrapper.py sample()).  A step here = lanes x B images.
         model.lanes = args.lanes
         cond2 = [CLASSES[(rank * B + i) % len(CLASSES)] for i in range(args.lanes * B)]
         args2 = argparse.Namespace(**vars(args))      # an extra block: at most 4 timed steps after at most 3 warm-up steps
@@ -417,9 +417,9 @@ def run_taming(args, rank, world, dev, L, peaks):
         b2.update({"metric": METRIC.replace("batch 16/GPU", f"{args.lanes} concurrent batches of 16/GPU"), "dtype": blk["dtype"],
                    "config": dict(blk["config"], workload=f"taming_cin_{args.lanes}xB16_concurrent_lanes_wm_linear_h1_d2_g0.25",
                                   batch_per_gpu=args.lanes * B, global_batch=args.lanes * B * world, lanes=args.lanes,
-                                  note="NOT the headline configuration: the wrapper's sample() is given 2 x 16 conditionings and "
-                                       "runs the two batches of 16 on two engine lanes / CUDA streams; ids identical to the "
-                                       "sequential chunk loop (tests/test_gpu_watermark.py)")})
+                                  note=f"NOT the headline configuration: the wrapper's sample() is given {args.lanes} x 16 conditionings and "
+                                       f"runs the {args.lanes} batches of 16 on {args.lanes} engine lanes / CUDA streams; ids identical "
+                                       "to the sequential chunk loop (tests/test_gpu_watermark.py)")})
         blk["_lanes_block"] = b2
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         gs = {k[len("transformer."):]: v.cpu() for k, v in state.items() if k.startswith("transformer.")}
