@@ -309,59 +309,83 @@ __global__ void __launch_bounds__(256, 3) conv_in3_kernel(const ConvInArgs a) {
 
 // ------------------------------------------------------------------------------------------- AttnBlock core
 // out[b][i][:] = sum_j softmax_j(q_i . k_j * C^-0.5) v_j ; q,k,v,out NHWC [B][N][C].  grid (N/16, B), 256 threads.
+// Round 2: register tiles that halve / quarter the shared-memory reads per FMA (the first version issued one broadcast
+// LDS per 4 FMAs and ran at 126 GB/s, 200 us per launch): q.k^T as 2 keys x 8 queries per thread, the probabilities
+// stored key-major [N][16] so that p.v reads them as four LDS.128 per key for 2 channels x 16 queries of FMAs.
 constexpr int AB_Q = 16;
 __global__ void __launch_bounds__(256) attn_block_kernel(const float *__restrict__ q, const float *__restrict__ k,
                                                          const float *__restrict__ v, float *__restrict__ out, int N,
                                                          int C) {
     extern __shared__ __align__(16) float sm[];
     float *qs = sm;               // [AB_Q][C]
-    float *ps = sm + AB_Q * C;    // [AB_Q][N]
+    float *ps = sm + AB_Q * C;    // [N][AB_Q]  (key-major)
     const int b = blockIdx.y, i0 = blockIdx.x * AB_Q, tid = threadIdx.x;
     const float *qb = q + ((size_t)b * N + i0) * C;
     for (int i = tid; i < AB_Q * C / 4; i += 256) reinterpret_cast<float4 *>(qs)[i] = reinterpret_cast<const float4 *>(qb)[i];
     __syncthreads();
     const float scale = 1.0f / sqrtf((float)C);  // int(c)**(-0.5)
-    for (int j = tid; j < N; j += 256) {
-        const float *kj = k + ((size_t)b * N + j) * C;
-        float acc[AB_Q];
+    // ---- scores: thread = (key pair, query half); keys j and j + 128 * ceil, queries qh * 8 .. qh * 8 + 7 ----
+    const int qh = tid & 1, kp = tid >> 1;         // 128 key pairs per sweep, 2 query halves
+    for (int j0 = kp; j0 < N; j0 += 256) {
+        const int j1 = j0 + 128;
+        const bool has1 = j1 < N;
+        const float *ka = k + ((size_t)b * N + j0) * C;
+        const float *kb = k + ((size_t)b * N + (has1 ? j1 : j0)) * C;
+        float acc0[8], acc1[8];
 #pragma unroll
-        for (int i = 0; i < AB_Q; i++) acc[i] = 0.f;
+        for (int i = 0; i < 8; i++) { acc0[i] = 0.f; acc1[i] = 0.f; }
         for (int c = 0; c < C; c += 4) {
-            float4 k4 = *reinterpret_cast<const float4 *>(kj + c);
+            const float4 a4 = *reinterpret_cast<const float4 *>(ka + c);
+            const float4 b4 = *reinterpret_cast<const float4 *>(kb + c);
 #pragma unroll
-            for (int i = 0; i < AB_Q; i++) {
-                float4 q4 = *reinterpret_cast<const float4 *>(qs + i * C + c);
-                acc[i] += q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+            for (int i = 0; i < 8; i++) {
+                const float4 q4 = *reinterpret_cast<const float4 *>(qs + (qh * 8 + i) * C + c);
+                acc0[i] += q4.x * a4.x + q4.y * a4.y + q4.z * a4.z + q4.w * a4.w;
+                acc1[i] += q4.x * b4.x + q4.y * b4.y + q4.z * b4.z + q4.w * b4.w;
             }
         }
 #pragma unroll
-        for (int i = 0; i < AB_Q; i++) ps[i * N + j] = acc[i] * scale;
+        for (int i = 0; i < 8; i++) {
+            ps[j0 * AB_Q + qh * 8 + i] = acc0[i] * scale;
+            if (has1) ps[j1 * AB_Q + qh * 8 + i] = acc1[i] * scale;
+        }
     }
     __syncthreads();
     // softmax per query row: 8 warps, 2 rows each
     const int lane = tid & 31, warp = tid >> 5;
     for (int i = warp; i < AB_Q; i += 8) {
         float m = -INFINITY;
-        for (int j = lane; j < N; j += 32) m = fmaxf(m, ps[i * N + j]);
+        for (int j = lane; j < N; j += 32) m = fmaxf(m, ps[j * AB_Q + i]);
         m = warp_max(m);
         float s = 0.f;
-        for (int j = lane; j < N; j += 32) { float e = expf(ps[i * N + j] - m); ps[i * N + j] = e; s += e; }
+        for (int j = lane; j < N; j += 32) { float e = expf(ps[j * AB_Q + i] - m); ps[j * AB_Q + i] = e; s += e; }
         s = warp_sum(s);
         const float inv = 1.0f / s;
-        for (int j = lane; j < N; j += 32) ps[i * N + j] *= inv;
+        for (int j = lane; j < N; j += 32) ps[j * AB_Q + i] *= inv;
     }
     __syncthreads();
-    for (int c = tid; c < C; c += 256) {
-        float acc[AB_Q];
+    // ---- out = P V: thread = channels c and c + 256 (same summation order over j as before) ----
+    for (int c = tid; c < C; c += 512) {
+        const bool has1 = c + 256 < C;
+        float acc0[AB_Q], acc1[AB_Q];
 #pragma unroll
-        for (int i = 0; i < AB_Q; i++) acc[i] = 0.f;
+        for (int i = 0; i < AB_Q; i++) { acc0[i] = 0.f; acc1[i] = 0.f; }
+        const float *vb = v + (size_t)b * N * C;
         for (int j = 0; j < N; j++) {
-            const float vv = v[((size_t)b * N + j) * C + c];
+            const float va = vb[(size_t)j * C + c];
+            const float vc = has1 ? vb[(size_t)j * C + c + 256] : 0.f;
 #pragma unroll
-            for (int i = 0; i < AB_Q; i++) acc[i] += ps[i * N + j] * vv;
+            for (int i4 = 0; i4 < AB_Q / 4; i4++) {
+                const float4 p4 = *reinterpret_cast<const float4 *>(ps + j * AB_Q + 4 * i4);
+                acc0[4 * i4] += p4.x * va; acc0[4 * i4 + 1] += p4.y * va; acc0[4 * i4 + 2] += p4.z * va; acc0[4 * i4 + 3] += p4.w * va;
+                acc1[4 * i4] += p4.x * vc; acc1[4 * i4 + 1] += p4.y * vc; acc1[4 * i4 + 2] += p4.z * vc; acc1[4 * i4 + 3] += p4.w * vc;
+            }
         }
 #pragma unroll
-        for (int i = 0; i < AB_Q; i++) out[((size_t)b * N + i0 + i) * C + c] = acc[i];
+        for (int i = 0; i < AB_Q; i++) {
+            out[((size_t)b * N + i0 + i) * C + c] = acc0[i];
+            if (has1) out[((size_t)b * N + i0 + i) * C + c + 256] = acc1[i];
+        }
     }
 }
 
